@@ -1,0 +1,728 @@
+// api.cu -- C ABI of libndconv_cuda.so (include/ndconv.h): processor handle, caches, planning, launches.
+//
+// Built by nvcc for sm_100a (the product).  tests/emul/ compiles the same translation unit with
+// -DNDCONV_HOST_EMUL as plain C++ to check the kernel bodies' index logic on a GPU-less box; that
+// build reports ndconv_is_emulation() == 1 and is refused by the product loader.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "host_logic.h"
+#include "kernels_direct.h"
+#include "kernels_fft.h"
+
+#ifdef NDCONV_CUDA
+#include <cuda_runtime.h>
+#endif
+
+using namespace ndc;
+
+#define NDCONV_VERSION_STRING "ndconv-b200 0.1.0 (sm_100a)"
+
+// ======================================================================================================
+// backend: CUDA runtime, or (tests only) host emulation
+// ======================================================================================================
+#ifdef NDCONV_CUDA
+typedef cudaStream_t stream_t;
+#define CU_CHECK(expr)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t _e = (expr);                                                                         \
+        if (_e != cudaSuccess) {                                                                         \
+            set_error(std::string("CUDA error: ") + cudaGetErrorString(_e) + " at " #expr);              \
+            return NDCONV_ERR_CUDA;                                                                      \
+        }                                                                                                \
+    } while (0)
+
+template <class Body, class Params> __global__ void __launch_bounds__(512) kentry(const __grid_constant__ Params p)
+{
+    extern __shared__ __align__(16) unsigned char ndc_smem[];
+    BlockCtx c;
+    c.tid = threadIdx.x; c.nt = blockDim.x; c.bid = blockIdx.x; c.nb = gridDim.x; c.smem = (char *)ndc_smem;
+    Body::run(c, p);
+}
+
+template <class Body, class Params>
+static int launch(stream_t st, int64_t grid, int block, size_t smem, const Params &p, int64_t *counter)
+{
+    static bool attr_set = false;
+    if (!attr_set) {
+        CU_CHECK(cudaFuncSetAttribute(kentry<Body, Params>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set = true;
+    }
+    if (grid < 1) grid = 1;
+    kentry<Body, Params><<<(unsigned)grid, block, smem, st>>>(p);
+    CU_CHECK(cudaGetLastError());
+    if (counter) (*counter)++;
+    return NDCONV_OK;
+}
+static int be_malloc(void **p, size_t n) { CU_CHECK(cudaMalloc(p, n ? n : 1)); return NDCONV_OK; }
+static void be_free(void *p) { if (p) cudaFree(p); }
+static int be_h2d(void *d, const void *s, size_t n, stream_t st) { CU_CHECK(cudaMemcpyAsync(d, s, n, cudaMemcpyHostToDevice, st)); return NDCONV_OK; }
+static int be_d2h(void *d, const void *s, size_t n, stream_t st) { CU_CHECK(cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToHost, st)); return NDCONV_OK; }
+static int be_sync(stream_t st) { CU_CHECK(cudaStreamSynchronize(st)); return NDCONV_OK; }
+static const int kMaxGridMult = 8;
+static int be_num_sms(int dev) { int n = 148; cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); return n; }
+#else
+typedef void *stream_t;
+#define CU_CHECK(expr) do { } while (0)
+template <class Body, class Params>
+static int launch(stream_t, int64_t grid, int, size_t smem, const Params &p, int64_t *counter)
+{
+    std::vector<unsigned char> sm(smem + 64);
+    if (grid < 1) grid = 1;
+    // one block walks the whole grid-stride loop; a second "block" exercises the nb > 1 indexing
+    int64_t nb = grid > 1 ? 2 : 1;
+    for (int64_t b = 0; b < nb; b++) {
+        BlockCtx c; c.tid = 0; c.nt = 1; c.bid = b; c.nb = nb; c.smem = (char *)sm.data();
+        Body::run(c, p);
+    }
+    if (counter) (*counter)++;
+    return NDCONV_OK;
+}
+static int be_malloc(void **p, size_t n) { *p = malloc(n ? n : 1); return *p ? NDCONV_OK : NDCONV_ERR_INTERNAL; }
+static void be_free(void *p) { free(p); }
+static int be_h2d(void *d, const void *s, size_t n, stream_t) { memcpy(d, s, n); return NDCONV_OK; }
+static int be_d2h(void *d, const void *s, size_t n, stream_t) { memcpy(d, s, n); return NDCONV_OK; }
+static int be_sync(stream_t) { return NDCONV_OK; }
+static const int kMaxGridMult = 1;
+static int be_num_sms(int) { return 4; }
+#endif
+
+// ======================================================================================================
+// processor
+// ======================================================================================================
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t n)
+    {
+        if (n <= cap) return NDCONV_OK;
+        be_free(p); p = nullptr; cap = 0;
+        size_t want = n + n / 8;
+        int st = be_malloc(&p, want);
+        if (st) return st;
+        cap = want;
+        return NDCONV_OK;
+    }
+    void release() { be_free(p); p = nullptr; cap = 0; }
+};
+
+struct KSpecEntry {
+    std::vector<unsigned char> key;
+    DevBuf buf;
+    uint64_t last_use = 0;
+};
+
+struct ndconv_processor {
+    int device = 0;
+    int num_sms = 148;
+    stream_t own_stream = nullptr, stream = nullptr;
+    int64_t launches = 0;
+    DevBuf ws, in_stage, out_stage, meta, kb_stage, kmeta;
+    std::map<std::pair<int, int>, void *> tw_c;   // (L, is_double) -> exp(-2 pi i j/L), j < L
+    std::map<std::pair<int, int>, void *> tw_r;   // (F, is_double) -> exp(-2 pi i k/F), k <= F/4 + 1
+    std::vector<std::unique_ptr<KSpecEntry>> kspecs;
+    uint64_t tick = 0;
+    size_t held() const
+    {
+        size_t s = ws.cap + in_stage.cap + out_stage.cap + meta.cap + kb_stage.cap + kmeta.cap;
+        for (auto &k : kspecs) s += k->buf.cap;
+        return s;
+    }
+};
+
+static int set_device(const ndconv_processor *p)
+{
+#ifdef NDCONV_CUDA
+    CU_CHECK(cudaSetDevice(p->device));
+#else
+    (void)p;
+#endif
+    return NDCONV_OK;
+}
+
+template <class R> static int get_tw_c(ndconv_processor *p, int L, const cx<R> **out)
+{
+    auto key = std::make_pair(L, (int)(sizeof(R) == 8));
+    auto it = p->tw_c.find(key);
+    if (it == p->tw_c.end()) {
+        std::vector<cx<R>> h((size_t)std::max(L, 1));
+        for (int j = 0; j < L; j++) {
+            long double a = -2.0L * 3.14159265358979323846264338327950288L * (long double)j / (long double)L;
+            h[j].re = (R)cosl(a); h[j].im = (R)sinl(a);
+        }
+        void *d = nullptr;
+        int st = be_malloc(&d, h.size() * sizeof(cx<R>)); if (st) return st;
+        st = be_h2d(d, h.data(), h.size() * sizeof(cx<R>), p->stream); if (st) return st;
+        st = be_sync(p->stream); if (st) return st;
+        it = p->tw_c.emplace(key, d).first;
+    }
+    *out = (const cx<R> *)it->second;
+    return NDCONV_OK;
+}
+template <class R> static int get_tw_r(ndconv_processor *p, int F, const cx<R> **out)
+{
+    auto key = std::make_pair(F, (int)(sizeof(R) == 8));
+    auto it = p->tw_r.find(key);
+    if (it == p->tw_r.end()) {
+        int cnt = F / 4 + 2;
+        std::vector<cx<R>> h((size_t)cnt);
+        for (int k = 0; k < cnt; k++) {
+            long double a = -2.0L * 3.14159265358979323846264338327950288L * (long double)k / (long double)F;
+            h[k].re = (R)cosl(a); h[k].im = (R)sinl(a);
+        }
+        void *d = nullptr;
+        int st = be_malloc(&d, h.size() * sizeof(cx<R>)); if (st) return st;
+        st = be_h2d(d, h.data(), h.size() * sizeof(cx<R>), p->stream); if (st) return st;
+        st = be_sync(p->stream); if (st) return st;
+        it = p->tw_r.emplace(key, d).first;
+    }
+    *out = (const cx<R> *)it->second;
+    return NDCONV_OK;
+}
+
+// pack a strided host array into standard layout
+static void pack_strided(const void *src, int ndim, const int64_t *shape, const int64_t *strides, int es, void *dst)
+{
+    int64_t total = 1;
+    for (int i = 0; i < ndim; i++) total *= shape[i];
+    int64_t idx[NDC_MAX_DIM] = {0};
+    const unsigned char *s = (const unsigned char *)src;
+    unsigned char *d = (unsigned char *)dst;
+    for (int64_t e = 0; e < total; e++) {
+        int64_t o = 0;
+        for (int i = 0; i < ndim; i++) o += idx[i] * strides[i];
+        memcpy(d + e * es, s + o * es, es);
+        for (int i = ndim - 1; i >= 0; i--) { if (++idx[i] < shape[i]) break; idx[i] = 0; }
+    }
+}
+
+// device copies of the per-axis border maps (+ optional tap tables) packed into one buffer
+struct MetaLayout {
+    size_t map_off[NDC_MAX_DIM];
+    size_t tap_off_off = 0, tap_lin_off = 0, tap_w_off = 0, total = 0;
+};
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static int upload_meta(ndconv_processor *p, DevBuf &buf, const Geom &g, const std::vector<int32_t> *maps, const Taps *taps, MetaLayout *ml)
+{
+    size_t off = 0;
+    for (int a = 0; a < g.ndim; a++) { ml->map_off[a] = off; off = align_up(off + maps[a].size() * sizeof(int32_t), 16); }
+    if (taps) {
+        ml->tap_off_off = off; off = align_up(off + taps->off.size() * sizeof(int32_t), 16);
+        ml->tap_lin_off = off; off = align_up(off + taps->lin.size() * sizeof(int64_t), 16);
+        ml->tap_w_off = off; off = align_up(off + taps->w.size(), 16);
+    }
+    ml->total = off;
+    std::vector<unsigned char> h(off ? off : 16, 0);
+    for (int a = 0; a < g.ndim; a++) memcpy(h.data() + ml->map_off[a], maps[a].data(), maps[a].size() * sizeof(int32_t));
+    if (taps && taps->ntap) {
+        memcpy(h.data() + ml->tap_off_off, taps->off.data(), taps->off.size() * sizeof(int32_t));
+        memcpy(h.data() + ml->tap_lin_off, taps->lin.data(), taps->lin.size() * sizeof(int64_t));
+        memcpy(h.data() + ml->tap_w_off, taps->w.data(), taps->w.size());
+    }
+    int st = buf.reserve(h.size()); if (st) return st;
+    return be_h2d(buf.p, h.data(), h.size(), p->stream);
+}
+
+static void fill_consts(const ndconv_problem *pr, int ndim, unsigned char cf[][16], unsigned char cb[][16])
+{
+    for (int a = 0; a < ndim; a++) {
+        memset(cf[a], 0, 16); memset(cb[a], 0, 16);
+        if (pr->border[a][0].type == NDCONV_BORDER_CONST) memcpy(cf[a], pr->border[a][0].value, 16);
+        if (pr->border[a][1].type == NDCONV_BORDER_CONST) memcpy(cb[a], pr->border[a][1].value, 16);
+    }
+}
+
+// stage the data array on the device (host problems) or use it in place (device problems)
+static int stage_input(ndconv_processor *p, const ndconv_problem *pr, Geom &g, const void **dev_x)
+{
+    if (pr->memory == NDCONV_MEM_DEVICE) { *dev_x = pr->data; return NDCONV_OK; }
+    size_t bytes = (size_t)g.data_total * g.es;
+    int st = p->in_stage.reserve(bytes); if (st) return st;
+    if (g.data_contiguous) {
+        st = be_h2d(p->in_stage.p, pr->data, bytes, p->stream); if (st) return st;
+    } else {
+        std::vector<unsigned char> tmp(bytes);
+        pack_strided(pr->data, g.ndim, g.n, g.xstr, g.es, tmp.data());
+        st = be_h2d(p->in_stage.p, tmp.data(), bytes, p->stream); if (st) return st;
+        st = be_sync(p->stream); if (st) return st;
+    }
+    int64_t s = 1;
+    for (int i = g.ndim - 1; i >= 0; i--) { g.xstr[i] = s; s *= g.n[i]; }
+    *dev_x = p->in_stage.p;
+    return NDCONV_OK;
+}
+
+// ======================================================================================================
+// direct convolution
+// ======================================================================================================
+template <class T> static int run_direct_t(ndconv_processor *p, const DirectParams &dp)
+{
+    int block = 256;
+    int64_t grid = std::min<int64_t>((dp.total + block - 1) / block, (int64_t)p->num_sms * 16 * kMaxGridMult);
+    return launch<DirectBody<T>, DirectParams>(p->stream, grid, block, 0, dp, &p->launches);
+}
+
+static int conv_direct_impl(ndconv_processor *p, const ndconv_problem *pr, void *out)
+{
+    Geom g; std::vector<int32_t> maps[NDC_MAX_DIM];
+    int st = check_problem(pr, NDCONV_PATH_DIRECT, &g, maps); if (st) return st;
+    if (!out) { set_error("null output pointer"); return NDCONV_ERR_BAD_ARG; }
+    st = set_device(p); if (st) return st;
+    // taps are expressed on the device-side strides of x, so stage first
+    const void *dev_x = nullptr;
+    st = stage_input(p, pr, g, &dev_x); if (st) return st;
+    std::vector<unsigned char> kpacked((size_t)g.kernel_total * g.es);
+    pack_strided(pr->kernel, g.ndim, g.k, g.kstr, g.es, kpacked.data());
+    { int64_t s = 1; for (int i = g.ndim - 1; i >= 0; i--) { g.kstr[i] = s; s *= g.k[i]; } }
+    Taps taps; build_taps(g, kpacked.data(), taps);
+    MetaLayout ml;
+    st = upload_meta(p, p->meta, g, maps, &taps, &ml); if (st) return st;
+
+    DirectParams dp; memset(&dp, 0, sizeof(dp));
+    dp.ndim = g.ndim; dp.ntap = taps.ntap; dp.x = dev_x; dp.total = g.out_total;
+    const unsigned char *mb = (const unsigned char *)p->meta.p;
+    for (int a = 0; a < g.ndim; a++) {
+        dp.xstr[a] = g.xstr[a]; dp.n[a] = g.n[a]; dp.P[a] = g.P[a]; dp.pf[a] = g.pf[a]; dp.Kd[a] = g.Kd[a]; dp.s[a] = g.s[a]; dp.O[a] = g.O[a];
+        dp.map[a] = (const int32_t *)(mb + ml.map_off[a]);
+    }
+    dp.tap_off = (const int32_t *)(mb + ml.tap_off_off);
+    dp.tap_lin = (const int64_t *)(mb + ml.tap_lin_off);
+    dp.tap_w = mb + ml.tap_w_off;
+    fill_consts(pr, g.ndim, dp.cfront, dp.cback);
+    size_t obytes = (size_t)g.out_total * g.es;
+    if (pr->memory == NDCONV_MEM_HOST) { st = p->out_stage.reserve(obytes); if (st) return st; dp.out = p->out_stage.p; }
+    else dp.out = out;
+
+    switch (g.dtype) {
+    case NDCONV_I8: case NDCONV_U8: st = run_direct_t<uint8_t>(p, dp); break;
+    case NDCONV_I16: case NDCONV_U16: st = run_direct_t<uint16_t>(p, dp); break;
+    case NDCONV_I32: case NDCONV_U32: st = run_direct_t<uint32_t>(p, dp); break;
+    case NDCONV_I64: case NDCONV_U64: st = run_direct_t<uint64_t>(p, dp); break;
+    case NDCONV_F32: st = run_direct_t<float>(p, dp); break;
+    case NDCONV_F64: st = run_direct_t<double>(p, dp); break;
+    case NDCONV_C32: st = run_direct_t<cx<float>>(p, dp); break;
+    case NDCONV_C64: st = run_direct_t<cx<double>>(p, dp); break;
+    default: set_error("dtype"); st = NDCONV_ERR_BAD_ARG;
+    }
+    if (st) return st;
+    if (pr->memory == NDCONV_MEM_HOST) {
+        st = be_d2h(out, p->out_stage.p, obytes, p->stream); if (st) return st;
+        st = be_sync(p->stream); if (st) return st;
+    }
+    return NDCONV_OK;
+}
+
+// ======================================================================================================
+// FFT convolution
+// ======================================================================================================
+static const size_t kRowSmemBudget = 96 * 1024;
+static const size_t kColSmemBudget = 128 * 1024;
+static int cap_last_axis(bool is_cx, bool is_dbl) { return is_cx ? (is_dbl ? 2048 : 4096) : (is_dbl ? 4096 : 8192); }
+static int cap_col_axis(bool is_dbl) { return is_dbl ? 512 : 1024; }
+
+struct FftPlan {
+    int N = 0;
+    bool is_cx = false;
+    AxisTiling tl[NDC_MAX_DIM];
+    FftLen fl[NDC_MAX_DIM];       // complex transform per axis (last axis: F/2 for real input)
+    int H = 0, Hp = 0;
+    int64_t rows_per_tile = 1, tile_elems = 0, ntiles_total = 1;
+};
+
+static int make_plan(const Geom &g, FftPlan *pl)
+{
+    const int N = g.ndim;
+    const bool is_cx = dtype_is_complex(g.dtype), is_dbl = (g.dtype == NDCONV_F64 || g.dtype == NDCONV_C64);
+    pl->N = N; pl->is_cx = is_cx;
+    for (int a = 0; a < N; a++) {
+        const bool last = (a == N - 1);
+        const bool real_axis = last && !is_cx;
+        int cap = last ? cap_last_axis(is_cx, is_dbl) : cap_col_axis(is_dbl);
+        int st = plan_axis(g.P[a], g.Kd[a], cap, real_axis, &pl->tl[a]); if (st) return st;
+        int L = real_axis ? pl->tl[a].F / 2 : pl->tl[a].F;
+        if (!factor_radices(L, &pl->fl[a])) { set_error("internal: non-smooth FFT length"); return NDCONV_ERR_INTERNAL; }
+    }
+    const int Fl = pl->tl[N - 1].F;
+    pl->H = is_cx ? Fl : Fl / 2 + 1;
+    pl->Hp = (int)align_up((size_t)pl->H, 16);
+    pl->rows_per_tile = 1; pl->ntiles_total = 1;
+    for (int a = 0; a < N - 1; a++) pl->rows_per_tile *= pl->tl[a].F;
+    for (int a = 0; a < N; a++) pl->ntiles_total *= pl->tl[a].ntiles;
+    pl->tile_elems = pl->rows_per_tile * pl->Hp;
+    return NDCONV_OK;
+}
+
+template <class R> static int fill_plan_dev(ndconv_processor *p, const FftLen &fl, FftPlanDev<R> *d)
+{
+    d->L = fl.L; d->npass = fl.npass;
+    for (int i = 0; i < NDC_MAX_PASS; i++) d->radix[i] = i < fl.npass ? fl.radix[i] : 1;
+    return get_tw_c<R>(p, fl.L, &d->tw);
+}
+
+static int pick_rows_per_block(int L, size_t csz)
+{
+    int B = std::max(1, 1024 / std::max(L, 1));
+    B = std::min(B, 16);
+    while (B > 1 && 2 * (size_t)B * (L + 1) * csz + (size_t)B * 64 > kRowSmemBudget) B--;
+    return B;
+}
+static int pick_block_threads(int64_t butterflies)
+{
+    int t = (int)std::min<int64_t>(512, std::max<int64_t>(64, (butterflies + 31) / 32 * 32));
+    return t;
+}
+
+template <class R>
+static int run_row(ndconv_processor *p, int kind /*0 fwd 1 inv 2 1d*/, RowParams<R> &rp, int64_t out_rows)
+{
+    const size_t csz = sizeof(cx<R>);
+    const int L = rp.plan.L;
+    if (kind == 2) rp.B = 1;
+    else rp.B = pick_rows_per_block(L, csz);
+    size_t smem = 2 * (size_t)rp.B * (L + 1) * csz + (size_t)rp.B * 64 + 64;
+    if (smem > 227 * 1024) { set_error("internal: row kernel shared memory"); return NDCONV_ERR_INTERNAL; }
+    int N = rp.ndim;
+    int64_t ntiles_total = 1;
+    for (int a = 0; a < N; a++) ntiles_total *= rp.ntiles[a];
+    if (kind == 0) rp.nwork = ntiles_total * ((rp.rows_per_tile + rp.B - 1) / rp.B);
+    else if (kind == 1) rp.nwork = ((out_rows + rp.B - 1) / rp.B) * rp.ntiles[N - 1];
+    else rp.nwork = rp.ntiles[0];
+    int block = pick_block_threads((int64_t)rp.B * std::max(L / 4, 1));
+    int64_t grid = std::min<int64_t>(rp.nwork, (int64_t)p->num_sms * 4 * kMaxGridMult);
+    if (kind == 0) return launch<RowFwdBody<R>, RowParams<R>>(p->stream, grid, block, smem, rp, &p->launches);
+    if (kind == 1) return launch<RowInvBody<R>, RowParams<R>>(p->stream, grid, block, smem, rp, &p->launches);
+    return launch<Row1DBody<R>, RowParams<R>>(p->stream, grid, block, smem, rp, &p->launches);
+}
+
+template <class R>
+static int run_col(ndconv_processor *p, const FftPlan &pl, int axis, int mode, cx<R> *ws, const cx<R> *kspec, int64_t ntiles_total)
+{
+    ColParams<R> cp; memset(&cp, 0, sizeof(cp));
+    cp.ws = ws; cp.kspec = kspec; cp.F = pl.tl[axis].F; cp.mode = mode;
+    cp.outer = 1; cp.inner = pl.Hp;
+    for (int b = 0; b < axis; b++) cp.outer *= pl.tl[b].F;
+    for (int b = axis + 1; b < pl.N - 1; b++) cp.inner *= pl.tl[b].F;
+    cp.tile_elems = pl.tile_elems; cp.ntiles_total = ntiles_total;
+    int st = fill_plan_dev<R>(p, pl.fl[axis], &cp.plan); if (st) return st;
+    int W = 16;
+    while (W > 1 && 2 * (size_t)cp.F * W * sizeof(cx<R>) > kColSmemBudget) W >>= 1;
+    cp.W = W;
+    cp.nwork = ntiles_total * cp.outer * (cp.inner / W);
+    size_t smem = 2 * (size_t)cp.F * W * sizeof(cx<R>) + 64;
+    int block = pick_block_threads((int64_t)cp.F * W / 4);
+    int64_t grid = std::min<int64_t>(cp.nwork, (int64_t)p->num_sms * 4 * kMaxGridMult);
+    return launch<ColBody<R>, ColParams<R>>(p->stream, grid, block, smem, cp, &p->launches);
+}
+
+// kernel spectrum (cached per processor): conv_fft::padding::kernel (src/conv_fft/padding.rs:78-111) + forward
+template <class R>
+static int get_kernel_spectrum(ndconv_processor *p, const ndconv_problem *pr, const Geom &g, const FftPlan &pl, const cx<R> **out)
+{
+    const int N = g.ndim;
+    std::vector<unsigned char> kpacked((size_t)g.kernel_total * g.es);
+    pack_strided(pr->kernel, N, g.k, g.kstr, g.es, kpacked.data());
+    // cache key
+    std::vector<unsigned char> key;
+    auto push = [&](const void *d, size_t n) { key.insert(key.end(), (const unsigned char *)d, (const unsigned char *)d + n); };
+    int hdr[3] = {g.dtype, N, g.reverse ? 1 : 0};
+    push(hdr, sizeof(hdr));
+    for (int a = 0; a < N; a++) { int64_t v[3] = {g.k[a], g.d[a], (int64_t)pl.tl[a].F}; push(v, sizeof(v)); }
+    push(kpacked.data(), kpacked.size());
+    p->tick++;
+    for (auto &e : p->kspecs) if (e->key == key) { e->last_use = p->tick; *out = (const cx<R> *)e->buf.p; return NDCONV_OK; }
+
+    // dense dilated (and, for no_reverse, flipped) kernel of extent Kd, pre-scaled by 1/prod(F) (the reference divides
+    // after the inverse transform: real.rs:278-279, complex.rs:141-142)
+    int64_t kdtot = 1, kdstr[NDC_MAX_DIM];
+    for (int a = N - 1; a >= 0; a--) { kdstr[a] = kdtot; kdtot *= g.Kd[a]; }
+    long double scale = 1.0L;
+    for (int a = 0; a < N; a++) scale /= (long double)pl.tl[a].F;
+    const int nc = pl.is_cx ? 2 : 1;
+    std::vector<R> kb((size_t)kdtot * nc, (R)0);
+    {
+        int64_t idx[NDC_MAX_DIM] = {0};
+        const R *ks = (const R *)kpacked.data();
+        for (int64_t e = 0; e < g.kernel_total; e++) {
+            int64_t o = 0;
+            for (int a = 0; a < N; a++) o += (g.reverse ? idx[a] * g.d[a] : g.Kd[a] - 1 - idx[a] * g.d[a]) * kdstr[a];   // padding.rs:98-108
+            for (int c = 0; c < nc; c++) kb[(size_t)o * nc + c] = (R)((long double)ks[(size_t)e * nc + c] * scale);
+            for (int a = N - 1; a >= 0; a--) { if (++idx[a] < g.k[a]) break; idx[a] = 0; }
+        }
+    }
+    int st = p->kb_stage.reserve(kb.size() * sizeof(R)); if (st) return st;
+    st = be_h2d(p->kb_stage.p, kb.data(), kb.size() * sizeof(R), p->stream); if (st) return st;
+
+    // identity maps of length Kd
+    Geom kg = g;
+    std::vector<int32_t> kmaps[NDC_MAX_DIM];
+    for (int a = 0; a < N; a++) { kmaps[a].resize((size_t)g.Kd[a]); for (int64_t i = 0; i < g.Kd[a]; i++) kmaps[a][(size_t)i] = (int32_t)i; }
+    MetaLayout ml;
+    st = upload_meta(p, p->kmeta, kg, kmaps, nullptr, &ml); if (st) return st;
+
+    std::unique_ptr<KSpecEntry> ent(new KSpecEntry());
+    ent->key = key; ent->last_use = p->tick;
+    st = ent->buf.reserve((size_t)pl.tile_elems * sizeof(cx<R>)); if (st) return st;
+
+    RowParams<R> rp; memset(&rp, 0, sizeof(rp));
+    rp.ndim = N; rp.is_cx = pl.is_cx ? 1 : 0;
+    for (int a = 0; a < N; a++) {
+        rp.n[a] = g.Kd[a]; rp.xstr[a] = kdstr[a]; rp.P[a] = g.Kd[a];
+        rp.map[a] = (const int32_t *)((const unsigned char *)p->kmeta.p + ml.map_off[a]);
+        rp.F[a] = pl.tl[a].F; rp.V[a] = pl.tl[a].F; rp.ntiles[a] = 1; rp.Kd[a] = 1; rp.s[a] = 1; rp.O[a] = 1;
+    }
+    rp.x = p->kb_stage.p; rp.ws = (cx<R> *)ent->buf.p; rp.H = pl.H; rp.Hp = pl.Hp;
+    rp.rows_per_tile = pl.rows_per_tile; rp.tile_elems = pl.tile_elems;
+    st = fill_plan_dev<R>(p, pl.fl[N - 1], &rp.plan); if (st) return st;
+    if (!pl.is_cx) { st = get_tw_r<R>(p, pl.tl[N - 1].F, &rp.twr); if (st) return st; }
+    st = run_row<R>(p, 0, rp, 0); if (st) return st;
+    for (int a = N - 2; a >= 0; a--) { st = run_col<R>(p, pl, a, 0, (cx<R> *)ent->buf.p, nullptr, 1); if (st) return st; }
+    // the staging buffers are reused by the next build: make sure this one has been consumed
+    st = be_sync(p->stream); if (st) return st;
+
+    if (p->kspecs.size() >= 8) {   // small LRU
+        size_t victim = 0;
+        for (size_t i = 1; i < p->kspecs.size(); i++) if (p->kspecs[i]->last_use < p->kspecs[victim]->last_use) victim = i;
+        p->kspecs[victim]->buf.release();
+        p->kspecs.erase(p->kspecs.begin() + victim);
+    }
+    *out = (const cx<R> *)ent->buf.p;
+    p->kspecs.push_back(std::move(ent));
+    return NDCONV_OK;
+}
+
+template <class R>
+static int conv_fft_t(ndconv_processor *p, const ndconv_problem *pr, Geom &g, std::vector<int32_t> *maps, void *out)
+{
+    const int N = g.ndim;
+    FftPlan pl;
+    int st = make_plan(g, &pl); if (st) return st;
+    const void *dev_x = nullptr;
+    st = stage_input(p, pr, g, &dev_x); if (st) return st;
+    MetaLayout ml;
+    st = upload_meta(p, p->meta, g, maps, nullptr, &ml); if (st) return st;
+    const cx<R> *kspec = nullptr;
+    st = get_kernel_spectrum<R>(p, pr, g, pl, &kspec); if (st) return st;
+
+    size_t obytes = (size_t)g.out_total * g.es;
+    void *dev_out = out;
+    if (pr->memory == NDCONV_MEM_HOST) { st = p->out_stage.reserve(obytes); if (st) return st; dev_out = p->out_stage.p; }
+
+    RowParams<R> rp; memset(&rp, 0, sizeof(rp));
+    rp.ndim = N; rp.is_cx = pl.is_cx ? 1 : 0;
+    for (int a = 0; a < N; a++) {
+        rp.n[a] = g.n[a]; rp.xstr[a] = g.xstr[a]; rp.P[a] = g.P[a];
+        rp.map[a] = (const int32_t *)((const unsigned char *)p->meta.p + ml.map_off[a]);
+        rp.F[a] = pl.tl[a].F; rp.V[a] = pl.tl[a].V; rp.ntiles[a] = pl.tl[a].ntiles; rp.Kd[a] = (int)g.Kd[a];
+        rp.s[a] = g.s[a]; rp.O[a] = g.O[a];
+    }
+    fill_consts(pr, N, rp.cfront, rp.cback);
+    rp.x = dev_x; rp.out = dev_out; rp.kspec = kspec; rp.H = pl.H; rp.Hp = pl.Hp;
+    rp.rows_per_tile = pl.rows_per_tile; rp.tile_elems = pl.tile_elems;
+    st = fill_plan_dev<R>(p, pl.fl[N - 1], &rp.plan); if (st) return st;
+    if (!pl.is_cx) { st = get_tw_r<R>(p, pl.tl[N - 1].F, &rp.twr); if (st) return st; }
+
+    if (N == 1) {
+        st = run_row<R>(p, 2, rp, 1); if (st) return st;
+    } else {
+        st = p->ws.reserve((size_t)pl.ntiles_total * pl.tile_elems * sizeof(cx<R>)); if (st) return st;
+        rp.ws = (cx<R> *)p->ws.p;
+        st = run_row<R>(p, 0, rp, 0); if (st) return st;
+        for (int a = N - 2; a >= 1; a--) { st = run_col<R>(p, pl, a, 0, rp.ws, nullptr, pl.ntiles_total); if (st) return st; }
+        st = run_col<R>(p, pl, 0, 2, rp.ws, kspec, pl.ntiles_total); if (st) return st;
+        for (int a = 1; a <= N - 2; a++) { st = run_col<R>(p, pl, a, 1, rp.ws, nullptr, pl.ntiles_total); if (st) return st; }
+        int64_t out_rows = 1;
+        for (int a = 0; a < N - 1; a++) out_rows *= g.O[a];
+        st = run_row<R>(p, 1, rp, out_rows); if (st) return st;
+    }
+    if (pr->memory == NDCONV_MEM_HOST) {
+        st = be_d2h(out, dev_out, obytes, p->stream); if (st) return st;
+        st = be_sync(p->stream); if (st) return st;
+    }
+    return NDCONV_OK;
+}
+
+static int conv_fft_impl(ndconv_processor *p, const ndconv_problem *pr, void *out)
+{
+    Geom g; std::vector<int32_t> maps[NDC_MAX_DIM];
+    int st = check_problem(pr, NDCONV_PATH_FFT, &g, maps); if (st) return st;
+    if (!out) { set_error("null output pointer"); return NDCONV_ERR_BAD_ARG; }
+    st = set_device(p); if (st) return st;
+    if (g.dtype == NDCONV_F32 || g.dtype == NDCONV_C32) return conv_fft_t<float>(p, pr, g, maps, out);
+    return conv_fft_t<double>(p, pr, g, maps, out);
+}
+
+// ======================================================================================================
+// C ABI
+// ======================================================================================================
+extern "C" {
+
+const char *ndconv_version(void) { return NDCONV_VERSION_STRING; }
+int ndconv_is_emulation(void)
+{
+#ifdef NDCONV_CUDA
+    return 0;
+#else
+    return 1;
+#endif
+}
+const char *ndconv_last_error_string(void) { return get_error(); }
+const char *ndconv_status_string(int s)
+{
+    switch (s) {
+    case NDCONV_OK: return "ok";
+    case NDCONV_ERR_DATA_SHAPE: return "DataShape";
+    case NDCONV_ERR_KERNEL_SHAPE: return "KernelShape";
+    case NDCONV_ERR_MISMATCH_SHAPE: return "MismatchShape";
+    case NDCONV_ERR_PANIC: return "ReferencePanic";
+    case NDCONV_ERR_BAD_ARG: return "BadArgument";
+    case NDCONV_ERR_UNSUPPORTED: return "Unsupported";
+    case NDCONV_ERR_CUDA: return "CudaError";
+    case NDCONV_ERR_INTERNAL: return "InternalError";
+    }
+    return "unknown";
+}
+size_t ndconv_dtype_size(int dtype) { return dtype_size(dtype); }
+
+int ndconv_device_count(void)
+{
+#ifdef NDCONV_CUDA
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { set_error(std::string("CUDA error: ") + cudaGetErrorString(e)); cudaGetLastError(); return -NDCONV_ERR_CUDA; }
+    return n;
+#else
+    return 1;
+#endif
+}
+
+int ndconv_unfold_conv_mode(int mode, int ndim, const int64_t *kernel_shape, const int64_t *dilation, const int64_t *padding,
+                            const int64_t *strides, int64_t out_pad[][2], int64_t *out_stride)
+{
+    return unfold_mode(mode, ndim, kernel_shape, dilation, padding, strides, out_pad, out_stride);
+}
+int64_t ndconv_good_fft_size(int64_t n) { return good_size_cc(n); }
+int64_t ndconv_plan_fft_size(int64_t n, int real_axis) { return smooth_ge(n, real_axis != 0); }
+
+int ndconv_out_shape(const ndconv_problem *problem, int path, int64_t *out_shape)
+{
+    Geom g; std::vector<int32_t> maps[NDC_MAX_DIM];
+    int st = check_problem(problem, path, &g, maps); if (st) return st;
+    if (out_shape) for (int i = 0; i < g.ndim; i++) out_shape[i] = g.O[i];
+    return NDCONV_OK;
+}
+
+int ndconv_border_index_map(int64_t n, int64_t pad_front, int64_t pad_back, int border_front, int border_back, int32_t *out_map)
+{
+    std::vector<int32_t> m;
+    int st = build_border_map(n, pad_front, pad_back, border_front, border_back, m); if (st) return st;
+    if (out_map) memcpy(out_map, m.data(), m.size() * sizeof(int32_t));
+    return NDCONV_OK;
+}
+
+int ndconv_processor_create(int device, ndconv_processor **out)
+{
+    if (!out) { set_error("null out"); return NDCONV_ERR_BAD_ARG; }
+    *out = nullptr;
+    std::unique_ptr<ndconv_processor> p(new ndconv_processor());
+    p->device = device;
+#ifdef NDCONV_CUDA
+    int n = 0;
+    CU_CHECK(cudaGetDeviceCount(&n));
+    if (device < 0 || device >= n) { set_error("no such CUDA device"); return NDCONV_ERR_CUDA; }
+    CU_CHECK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU_CHECK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) { set_error(std::string("device is not sm_100 (Blackwell B200): ") + prop.name + "; this library has no other code path"); return NDCONV_ERR_CUDA; }
+    CU_CHECK(cudaStreamCreateWithFlags(&p->own_stream, cudaStreamNonBlocking));
+#endif
+    p->stream = p->own_stream;
+    p->num_sms = be_num_sms(device);
+    *out = p.release();
+    return NDCONV_OK;
+}
+
+int ndconv_processor_destroy(ndconv_processor *p)
+{
+    if (!p) return NDCONV_OK;
+    set_device(p);
+    be_sync(p->stream);
+    p->ws.release(); p->in_stage.release(); p->out_stage.release(); p->meta.release(); p->kb_stage.release(); p->kmeta.release();
+    for (auto &kv : p->tw_c) be_free(kv.second);
+    for (auto &kv : p->tw_r) be_free(kv.second);
+    for (auto &k : p->kspecs) k->buf.release();
+#ifdef NDCONV_CUDA
+    if (p->own_stream) cudaStreamDestroy(p->own_stream);
+#endif
+    delete p;
+    return NDCONV_OK;
+}
+
+int ndconv_processor_set_stream(ndconv_processor *p, void *cuda_stream)
+{
+    if (!p) { set_error("null processor"); return NDCONV_ERR_BAD_ARG; }
+    p->stream = cuda_stream ? (stream_t)cuda_stream : p->own_stream;
+    return NDCONV_OK;
+}
+int ndconv_processor_synchronize(ndconv_processor *p)
+{
+    if (!p) { set_error("null processor"); return NDCONV_ERR_BAD_ARG; }
+    int st = set_device(p); if (st) return st;
+    return be_sync(p->stream);
+}
+int64_t ndconv_processor_launch_count(const ndconv_processor *p) { return p ? p->launches : 0; }
+int64_t ndconv_processor_workspace_bytes(const ndconv_processor *p) { return p ? (int64_t)p->held() : 0; }
+
+static int with_processor(ndconv_processor *p, const ndconv_problem *pr, void *out, int (*fn)(ndconv_processor *, const ndconv_problem *, void *))
+{
+    if (p) return fn(p, pr, out);
+    if (pr && pr->memory == NDCONV_MEM_DEVICE) { set_error("device-resident problems need a processor"); return NDCONV_ERR_BAD_ARG; }
+    // validate before touching the device so shape errors surface exactly as in the reference
+    if (pr) { Geom g; std::vector<int32_t> maps[NDC_MAX_DIM]; int st = check_problem(pr, fn == conv_direct_impl ? NDCONV_PATH_DIRECT : NDCONV_PATH_FFT, &g, maps); if (st) return st; }
+    ndconv_processor *tmp = nullptr;
+    int st = ndconv_processor_create(0, &tmp); if (st) return st;
+    st = fn(tmp, pr, out);
+    std::string keep = get_error();
+    ndconv_processor_destroy(tmp);
+    set_error(keep);
+    return st;
+}
+
+int ndconv_conv_direct(ndconv_processor *p, const ndconv_problem *problem, void *out) { return with_processor(p, problem, out, conv_direct_impl); }
+int ndconv_conv_fft(ndconv_processor *p, const ndconv_problem *problem, void *out) { return with_processor(p, problem, out, conv_fft_impl); }
+int ndconv_conv_fft_par(ndconv_processor *p, const ndconv_problem *problem, void *out) { return with_processor(p, problem, out, conv_fft_impl); }
+
+int ndconv_slab_plan(const ndconv_problem *problem, int path, int n_slabs, int slab, ndconv_slab *out)
+{
+    Geom g; std::vector<int32_t> maps[NDC_MAX_DIM];
+    int st = check_problem(problem, path, &g, maps); if (st) return st;
+    return slab_plan(g, n_slabs, slab, out);
+}
+
+void *ndconv_host_alloc(size_t bytes)
+{
+#ifdef NDCONV_CUDA
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); set_error("cudaHostAlloc failed"); return nullptr; }
+    return p;
+#else
+    return malloc(bytes ? bytes : 1);
+#endif
+}
+void ndconv_host_free(void *ptr)
+{
+#ifdef NDCONV_CUDA
+    if (ptr) cudaFreeHost(ptr);
+#else
+    free(ptr);
+#endif
+}
+
+}  // extern "C"
