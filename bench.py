@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""bench.py -- conv_fft output Gsamples/s on the BASELINE.json workload.
+
+Workload (config.workload): BASELINE.json configs[4], the configuration the metric's "1/2/4/8 B200" and
+"HBM GB/s % of peak" are quoted on, and the largest that fits one GPU:
+    2-D conv_fft f32, x = (32768, 32768), k = (63, 63), ConvMode::Full, PaddingMode::Reflect  
+    -> out (32830, 32830) = 1.078 G samples per step.
+A step = one full convolution of the array.  With N > 1 ranks the OUTPUT rows of axis 0 are split into N
+overlap-save slabs (ndconv_slab_plan); every rank convolves its slab (input rows + (Kd0-1)-row halo) with no
+data-path collective -> strong scaling, total work fixed.
+
+  value : whole-job output samples/s, inputs resident in HBM, CUDA events on the launching stream, max over ranks
+  e2e   : same metric through the host-buffer C-ABI call (ndconv_conv_fft, NDCONV_MEM_HOST): pinned host input ->
+          H2D -> kernels -> D2H -> pinned host output, all inside the timed region
+  roofline : dominant kernel, algorithmic bytes / CUDA-event duration vs MEASURED_PEAKS.json
+  cpu_baseline / --impl reference : the oracle's scipy-pocketfft restatement of the reference pipeline
+          (good_size_cc buffers -> rfftn x2 -> multiply -> irfftn -> crop), all host cores, on a bounded row-slab
+          of the same workload.  kind "port": the reference is Rust and cannot be built in this image.
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+WORKLOADS = {
+    # name: (x shape, k shape, dilation, mode, padding)
+    "c5": dict(x=(32768, 32768), k=(63, 63), dil=1, mode="full", padding="reflect", dtype="float32",
+               desc="2D conv_fft f32 x=(32768,32768) k=(63,63) Full Reflect (BASELINE configs[4])"),
+    "c5s": dict(x=(8192, 8192), k=(63, 63), dil=1, mode="full", padding="reflect", dtype="float32",
+                desc="reduced c5 for quick checks (NOT the headline)"),
+}
+CPU_SAMPLE_ROWS = 4096   # rows of x in the bounded CPU sample
+
+
+def metric_name():
+    return "conv_fft output Gsamples/s"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) < 8:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def make_inputs(w, rows=None, seed_c=5):
+    """synthetic data as SURVEY 8d: default_rng(1000+c) / (2000+c), Uniform[0,1) f32"""
+    shape = list(w["x"])
+    if rows is not None:
+        shape[0] = rows
+    x = np.random.default_rng(1000 + seed_c).random(shape, dtype=np.float32)
+    k = np.random.default_rng(2000 + seed_c).random(w["k"], dtype=np.float32)
+    return x, k
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the oracle's scipy port on a bounded sample
+# ------------------------------------------------------------------------------------------------
+def cpu_sample(w, steps, warmup, workers):
+    from oracle import oracle
+    rows = min(CPU_SAMPLE_ROWS, w["x"][0])
+    x, k = make_inputs(w, rows=rows)
+    times = []
+    out = None
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        out = oracle.conv_fft_scipy(x, k, w["mode"], w["padding"], w["dil"], True, workers=workers)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    n_out = int(np.prod(out.shape))
+    t = float(np.mean(times))
+    return n_out / t / 1e9, t, f"{rows} of {w['x'][0]} input rows x {w['x'][1]} cols, same kernel/mode/border -> {n_out} output samples per step"
+
+
+def run_reference(args, w, rank, world):
+    if rank != 0:
+        return
+    workers = os.cpu_count() or 1
+    v, t, sample = cpu_sample(w, max(1, min(args.steps, 3)), 1 if args.warmup else 0, workers)
+    line = {
+        "impl": "reference", "metric": metric_name(), "value": v, "unit": "Gsamples/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": w["desc"], "sample": sample},
+        "cpu_baseline": {"value": v, "unit": "Gsamples/s", "cores": workers, "kind": "port", "sample": sample,
+                         "engine": "scipy.fft (pocketfft) restatement of src/conv_fft/mod.rs:229-289; the Rust reference cannot be built here"},
+        "e2e": {"value": v, "unit": "Gsamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_gpu(args, w, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    pkg = importlib.import_module("ndarray-conv_b200")
+    lib = pkg.get_library()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    kshape, dil = w["k"], w["dil"]
+    mode = {"full": pkg.ConvMode.Full, "same": pkg.ConvMode.Same, "valid": pkg.ConvMode.Valid}[w["mode"]]
+    pmode = {"reflect": pkg.PaddingMode.Reflect, "zeros": pkg.PaddingMode.Zeros, "replicate": pkg.PaddingMode.Replicate,
+             "circular": pkg.PaddingMode.Circular}[w["padding"]]
+    n0, n1 = w["x"]
+    k_host = np.random.default_rng(2005).random(kshape, dtype=np.float32)
+    kwd = pkg.with_dilation(k_host, dil)
+
+    # ---- slab of this rank (overlap-save along axis 0) ----
+    pads, strides = mode.unfold(kshape, [dil] * 2, lib)
+    sl = pkg.slab_plan((n0, n1), np.float32, kwd, mode, pmode, pkg.PATH_FFT, world, rank, lib)
+    Kd0 = (kshape[0] - 1) * dil + 1
+    pf0, pb0 = int(pads[0][0]), int(pads[0][1])
+    pb_, pe_ = sl["pad_begin"], sl["pad_end"]              # rows of the padded axis 0 this rank reads
+    src_lo, src_hi = max(pb_ - pf0, 0), min(pe_ - pf0, n0)  # input rows held by this rank (halo included)
+    slab_pf, slab_pb = max(pf0 - pb_, 0), max(pe_ - (pf0 + n0), 0)   # the true array edge falls inside the slab only at rank 0 / N-1
+    rows = src_hi - src_lo
+    explicit = ([[slab_pf, slab_pb], [int(pads[1][0]), int(pads[1][1])]], [int(strides[0]), int(strides[1])])
+    out_rows = sl["out_end"] - sl["out_begin"]
+    total_out = ((n0 + pf0 + pb0 - Kd0) // int(strides[0]) + 1) * ((n1 + int(pads[1][0]) + int(pads[1][1]) - ((kshape[1] - 1) * dil + 1)) // int(strides[1]) + 1)
+
+    # ---- synthetic input: pinned host slab + device copy ----
+    x_pin = torch.empty((rows, n1), dtype=torch.float32, pin_memory=True)
+    rng = np.random.default_rng(1005 + rank)
+    xv = x_pin.numpy()
+    step_rows = 2048
+    for r in range(0, rows, step_rows):
+        xv[r:r + step_rows] = rng.random((min(step_rows, rows - r), n1), dtype=np.float32)
+    x_dev = x_pin.to(dev, non_blocking=False)
+    proc = pkg.get_fft_processor(local_rank, lib)
+    stream = torch.cuda.current_stream(dev)
+    proc.set_stream(stream.cuda_stream)
+    oshape = pkg.conv_device("ndconv_conv_fft", proc, x_dev.data_ptr(), (rows, n1), (n1, 1), np.float32, kwd, mode, pmode, None, explicit=explicit)
+    assert oshape[0] == out_rows, (oshape, out_rows)
+    y_dev = torch.empty(oshape, dtype=torch.float32, device=dev)
+    y_pin = torch.empty(oshape, dtype=torch.float32, pin_memory=True)
+
+    def step_device():
+        pkg.conv_device("ndconv_conv_fft", proc, x_dev.data_ptr(), (rows, n1), (n1, 1), np.float32, kwd, mode, pmode, y_dev.data_ptr(), explicit=explicit)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- parity spot check against direct f64 evaluation (not timed) ----
+    step_device()
+    torch.cuda.synchronize(dev)
+    spot = spot_check(xv, k_host, y_dev, slab_pf, int(pads[1][0]), w["padding"], dil, rows, n1)
+
+    # ---- value: device-resident, CUDA events ----
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    barrier()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    l0 = proc.launch_count
+    lib.c.ndconv_processor_set_profiling(proc.handle, 1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_device()
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = proc.launch_count - l0
+    kprof = read_profile(lib, proc)
+    lib.c.ndconv_processor_set_profiling(proc.handle, 0)
+    clk = clocks.stop() if rank == 0 else None
+    t_dev = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
+    ms_max = float(t_dev.item())
+
+    # ---- e2e: host buffers through the C-ABI host call (H2D + kernels + D2H inside the timed region) ----
+    proc.set_stream(0)   # the host call synchronises on the processor's own stream
+    def step_host():
+        pr, keep = pkg.make_problem((rows, n1), (n1, 1), x_pin.data_ptr(), np.float32, kwd, mode, pmode, pkg.MEM_HOST, lib, explicit=explicit)
+        lib.check(lib.c.ndconv_conv_fft(proc.handle, pr, y_pin.data_ptr()))
+    import ctypes  # noqa
+    step_host()
+    e2e_steps = max(1, min(args.steps, 5))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        step_host()
+    barrier()
+    t_e2e = (time.perf_counter() - t0) / e2e_steps
+    t_e = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+    t_e2e = float(t_e.item())
+    h2d = torch.tensor([x_pin.numel() * 4 + k_host.nbytes], dtype=torch.float64, device=dev)
+    d2h = torch.tensor([y_pin.numel() * 4], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(h2d)
+        dist.all_reduce(d2h)
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        ms_step = ms_max / args.steps
+        value = total_out / (ms_step * 1e-3) / 1e9
+        compulsory = 4.0 * (n0 * n1 + kshape[0] * kshape[1] + total_out)      # SURVEY 8d alg_bytes (whole job)
+        roof = roofline_from_profile(kprof, args.steps, peak, peak_src)
+        cpu_v, cpu_t, cpu_s = cpu_sample(w, 1, 0, os.cpu_count() or 1) if world == 1 and not args.no_cpu else (None, None, None)
+        line = {
+            "metric": metric_name(), "value": value, "unit": "Gsamples/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": w["desc"], "out_samples_per_step": total_out, "parallelism": f"overlap-save slabs along axis 0 x{world}, no collective",
+                       "l2": "inputs (>= 0.5 GB per rank) are larger than the 126 MB L2; no explicit flush"},
+            "gpu_launches": int(launches),
+            "clocks": clk,
+            "e2e": {"value": total_out / t_e2e / 1e9, "unit": "Gsamples/s", "h2d_bytes_per_step": int(h2d.item()), "d2h_bytes_per_step": int(d2h.item()),
+                    "ms_per_step": t_e2e * 1e3, "api": "ndconv_conv_fft(NDCONV_MEM_HOST) on pinned host buffers"},
+            "roofline": roof,
+            "pipeline_compulsory": {"alg_bytes": compulsory, "achieved": compulsory / (ms_step * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                    "frac": compulsory / (ms_step * 1e-3) / 1e9 / peak, "note": "SURVEY 8d compulsory bytes (in+kernel+out) over the whole step"},
+            "kernels": kprof,
+            "parity_spot_check": spot,
+            "workspace_bytes": proc.workspace_bytes,
+        }
+        if cpu_v is not None:
+            line["cpu_baseline"] = {"value": cpu_v, "unit": "Gsamples/s", "cores": os.cpu_count() or 1, "kind": "port", "sample": cpu_s, "ms": cpu_t * 1e3}
+        print(json.dumps(line), flush=True)
+    proc.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def spot_check(x_host, k, y_dev, pf0, pf1, padding, dil, rows, n1, n=48):
+    """max |gpu - direct f64| over a few output samples of rank 0's slab, relative to max|out| (reflect / interior only)"""
+    import torch
+    rng = np.random.default_rng(1)
+    O0, O1 = y_dev.shape
+    Kd0, Kd1 = (k.shape[0] - 1) * dil + 1, (k.shape[1] - 1) * dil + 1
+    kf = k[::-1, ::-1].astype(np.float64)
+    worst, scale = 0.0, 0.0
+    def src(i, pf, nn):
+        j = i - pf
+        if padding == "reflect":
+            if j < 0:
+                j = -j
+            if j >= nn:
+                j = 2 * (nn - 1) - j
+        return j
+    pts = [(0, 0), (O0 - 1, O1 - 1), (0, O1 - 1), (O0 - 1, 0)] + [(int(rng.integers(0, O0)), int(rng.integers(0, O1))) for _ in range(n)]
+    yv = {p: float(y_dev[p[0], p[1]].item()) for p in pts}
+    for (o0, o1), got in yv.items():
+        r = [src(o0 + a * dil, pf0, rows) for a in range(k.shape[0])]
+        c = [src(o1 + b * dil, pf1, n1) for b in range(k.shape[1])]
+        if padding != "reflect" and (min(r) < 0 or max(r) >= rows or min(c) < 0 or max(c) >= n1):
+            continue
+        if min(r) < 0 or max(r) >= rows:
+            continue   # slab-interior edge (halo rows are real neighbours; not reflected) -- skip
+        ref = float(np.sum(x_host[np.ix_(r, c)].astype(np.float64) * kf))
+        worst = max(worst, abs(got - ref))
+        scale = max(scale, abs(ref))
+    return {"points": len(pts), "max_abs_err": worst, "max_abs_out": scale, "rel": worst / max(scale, 1e-30)}
+
+
+def read_profile(lib, proc):
+    import ctypes
+    names = (ctypes.c_char * 64 * 16)()
+    ms = (ctypes.c_double * 16)()
+    cnt = (ctypes.c_int64 * 16)()
+    by = (ctypes.c_double * 16)()
+    n = lib.c.ndconv_processor_get_profile(proc.handle, 16, names, ms, cnt, by)
+    out = []
+    for i in range(n):
+        out.append({"kernel": bytes(names[i]).split(b"\0")[0].decode(), "launches": int(cnt[i]), "total_ms": float(ms[i]),
+                    "alg_bytes_per_launch": float(by[i]) / max(int(cnt[i]), 1)})
+    return out
+
+
+def roofline_from_profile(kprof, steps, peak, peak_src):
+    if not kprof:
+        return None
+    top = max(kprof, key=lambda k: k["total_ms"])
+    avg_ms = top["total_ms"] / max(top["launches"], 1)
+    ach = top["alg_bytes_per_launch"] / (avg_ms * 1e-3) / 1e9
+    for k in kprof:
+        a = k["total_ms"] / max(k["launches"], 1)
+        k["avg_ms"] = a
+        k["achieved_gbs"] = k["alg_bytes_per_launch"] / (a * 1e-3) / 1e9 if a > 0 else None
+        k["frac_of_peak"] = k["achieved_gbs"] / peak if a > 0 else None
+    return {"bound": "hbm", "kernel": top["kernel"], "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+            "peak_source": peak_src, "avg_launch_ms": avg_ms, "alg_bytes_per_launch": top["alg_bytes_per_launch"]}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    w = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, w, rank, world)
+        return
+    run_gpu(args, w, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -143,6 +143,12 @@ int64_t ndconv_processor_launch_count(const ndconv_processor *p);
 /* bytes of device workspace currently held */
 int64_t ndconv_processor_workspace_bytes(const ndconv_processor *p);
 
+/* per-kernel device timing (CUDA events on the processor's stream around every launch) for bench.py's roofline:
+ * enable, run, then read the totals per kernel name since the last read.  alg_bytes = sum of the algorithmic bytes of the
+ * recorded launches.  Returns the number of entries written (<= max_entries). */
+int ndconv_processor_set_profiling(ndconv_processor *p, int enable);
+int ndconv_processor_get_profile(ndconv_processor *p, int max_entries, char (*names)[64], double *total_ms, int64_t *launches, double *alg_bytes);
+
 /* ---- the hot path ---------------------------------------------------------------------- */
 /* ConvExt::conv, src/conv/mod.rs:110-115,128-200.  `out`: contiguous standard-layout buffer of ndconv_out_shape()
  * elements, in the memory space named by problem->memory.  `p` may be NULL for host problems (a transient processor on device 0). */

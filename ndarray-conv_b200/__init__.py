@@ -82,6 +82,7 @@ EXPORTED_SYMBOLS = [
     "ndconv_device_count", "ndconv_unfold_conv_mode", "ndconv_good_fft_size", "ndconv_plan_fft_size", "ndconv_out_shape",
     "ndconv_border_index_map", "ndconv_processor_create", "ndconv_processor_destroy", "ndconv_processor_set_stream",
     "ndconv_processor_synchronize", "ndconv_processor_launch_count", "ndconv_processor_workspace_bytes",
+    "ndconv_processor_set_profiling", "ndconv_processor_get_profile",
     "ndconv_conv_direct", "ndconv_conv_fft", "ndconv_conv_fft_par", "ndconv_slab_plan", "ndconv_host_alloc", "ndconv_host_free",
 ]
 
@@ -114,6 +115,8 @@ class Library:
         c.ndconv_processor_launch_count.argtypes = [ctypes.c_void_p]
         c.ndconv_processor_workspace_bytes.restype = ctypes.c_int64
         c.ndconv_processor_workspace_bytes.argtypes = [ctypes.c_void_p]
+        c.ndconv_processor_set_profiling.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        c.ndconv_processor_get_profile.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
         for name in ("ndconv_conv_direct", "ndconv_conv_fft", "ndconv_conv_fft_par"):
             getattr(c, name).argtypes = [ctypes.c_void_p, ctypes.POINTER(_Problem), ctypes.c_void_p]
         c.ndconv_slab_plan.argtypes = [ctypes.POINTER(_Problem), ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(_Slab)]

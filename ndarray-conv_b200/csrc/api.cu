@@ -47,8 +47,17 @@ template <class Body, class Params> __global__ void __launch_bounds__(512) kentr
     Body::run(c, p);
 }
 
+struct ProfRec { const char *name; cudaEvent_t a, b; double bytes; };
+struct Profiler {
+    bool on = false;
+    std::vector<ProfRec> recs;
+    std::vector<cudaEvent_t> pool;
+    cudaEvent_t get() { if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; } cudaEvent_t e; cudaEventCreate(&e); return e; }
+};
+struct LaunchCtx { stream_t st; int64_t *counter; Profiler *prof; };
+
 template <class Body, class Params>
-static int launch(stream_t st, int64_t grid, int block, size_t smem, const Params &p, int64_t *counter)
+static int launch(const LaunchCtx &lc, const char *name, double alg_bytes, int64_t grid, int block, size_t smem, const Params &p)
 {
     static bool attr_set = false;
     if (!attr_set) {
@@ -56,9 +65,13 @@ static int launch(stream_t st, int64_t grid, int block, size_t smem, const Param
         attr_set = true;
     }
     if (grid < 1) grid = 1;
-    kentry<Body, Params><<<(unsigned)grid, block, smem, st>>>(p);
+    ProfRec rec;
+    const bool prof = lc.prof && lc.prof->on;
+    if (prof) { rec.name = name; rec.bytes = alg_bytes; rec.a = lc.prof->get(); rec.b = lc.prof->get(); CU_CHECK(cudaEventRecord(rec.a, lc.st)); }
+    kentry<Body, Params><<<(unsigned)grid, block, smem, lc.st>>>(p);
     CU_CHECK(cudaGetLastError());
-    if (counter) (*counter)++;
+    if (prof) { CU_CHECK(cudaEventRecord(rec.b, lc.st)); lc.prof->recs.push_back(rec); }
+    if (lc.counter) (*lc.counter)++;
     return NDCONV_OK;
 }
 static int be_malloc(void **p, size_t n) { CU_CHECK(cudaMalloc(p, n ? n : 1)); return NDCONV_OK; }
@@ -71,9 +84,12 @@ static int be_num_sms(int dev) { int n = 148; cudaDeviceGetAttribute(&n, cudaDev
 #else
 typedef void *stream_t;
 #define CU_CHECK(expr) do { } while (0)
+struct Profiler { bool on = false; };
+struct LaunchCtx { stream_t st; int64_t *counter; Profiler *prof; };
 template <class Body, class Params>
-static int launch(stream_t, int64_t grid, int, size_t smem, const Params &p, int64_t *counter)
+static int launch(const LaunchCtx &lc, const char *, double, int64_t grid, int, size_t smem, const Params &p)
 {
+    int64_t *counter = lc.counter;
     std::vector<unsigned char> sm(smem + 64);
     if (grid < 1) grid = 1;
     // one block walks the whole grid-stride loop; a second "block" exercises the nb > 1 indexing
@@ -129,6 +145,8 @@ struct ndconv_processor {
     std::map<std::pair<int, int>, void *> tw_r;   // (F, is_double) -> exp(-2 pi i k/F), k <= F/4 + 1
     std::vector<std::unique_ptr<KSpecEntry>> kspecs;
     uint64_t tick = 0;
+    Profiler prof;
+    LaunchCtx lc() { return LaunchCtx{stream, &launches, &prof}; }
     size_t held() const
     {
         size_t s = ws.cap + in_stage.cap + out_stage.cap + meta.cap + kb_stage.cap + kmeta.cap;
@@ -263,11 +281,11 @@ static int stage_input(ndconv_processor *p, const ndconv_problem *pr, Geom &g, c
 // ======================================================================================================
 // direct convolution
 // ======================================================================================================
-template <class T> static int run_direct_t(ndconv_processor *p, const DirectParams &dp)
+template <class T> static int run_direct_t(ndconv_processor *p, const DirectParams &dp, double alg_bytes)
 {
     int block = 256;
     int64_t grid = std::min<int64_t>((dp.total + block - 1) / block, (int64_t)p->num_sms * 16 * kMaxGridMult);
-    return launch<DirectBody<T>, DirectParams>(p->stream, grid, block, 0, dp, &p->launches);
+    return launch<DirectBody<T>, DirectParams>(p->lc(), "direct_conv", alg_bytes, grid, block, 0, dp);
 }
 
 static int conv_direct_impl(ndconv_processor *p, const ndconv_problem *pr, void *out)
@@ -301,15 +319,16 @@ static int conv_direct_impl(ndconv_processor *p, const ndconv_problem *pr, void 
     if (pr->memory == NDCONV_MEM_HOST) { st = p->out_stage.reserve(obytes); if (st) return st; dp.out = p->out_stage.p; }
     else dp.out = out;
 
+    const double alg_bytes = (double)g.es * ((double)g.data_total + (double)g.out_total + (double)taps.ntap);
     switch (g.dtype) {
-    case NDCONV_I8: case NDCONV_U8: st = run_direct_t<uint8_t>(p, dp); break;
-    case NDCONV_I16: case NDCONV_U16: st = run_direct_t<uint16_t>(p, dp); break;
-    case NDCONV_I32: case NDCONV_U32: st = run_direct_t<uint32_t>(p, dp); break;
-    case NDCONV_I64: case NDCONV_U64: st = run_direct_t<uint64_t>(p, dp); break;
-    case NDCONV_F32: st = run_direct_t<float>(p, dp); break;
-    case NDCONV_F64: st = run_direct_t<double>(p, dp); break;
-    case NDCONV_C32: st = run_direct_t<cx<float>>(p, dp); break;
-    case NDCONV_C64: st = run_direct_t<cx<double>>(p, dp); break;
+    case NDCONV_I8: case NDCONV_U8: st = run_direct_t<uint8_t>(p, dp, alg_bytes); break;
+    case NDCONV_I16: case NDCONV_U16: st = run_direct_t<uint16_t>(p, dp, alg_bytes); break;
+    case NDCONV_I32: case NDCONV_U32: st = run_direct_t<uint32_t>(p, dp, alg_bytes); break;
+    case NDCONV_I64: case NDCONV_U64: st = run_direct_t<uint64_t>(p, dp, alg_bytes); break;
+    case NDCONV_F32: st = run_direct_t<float>(p, dp, alg_bytes); break;
+    case NDCONV_F64: st = run_direct_t<double>(p, dp, alg_bytes); break;
+    case NDCONV_C32: st = run_direct_t<cx<float>>(p, dp, alg_bytes); break;
+    case NDCONV_C64: st = run_direct_t<cx<double>>(p, dp, alg_bytes); break;
     default: set_error("dtype"); st = NDCONV_ERR_BAD_ARG;
     }
     if (st) return st;
@@ -381,7 +400,7 @@ static int pick_block_threads(int64_t butterflies)
 }
 
 template <class R>
-static int run_row(ndconv_processor *p, int kind /*0 fwd 1 inv 2 1d*/, RowParams<R> &rp, int64_t out_rows)
+static int run_row(ndconv_processor *p, int kind /*0 fwd 1 inv 2 1d*/, RowParams<R> &rp, int64_t out_rows, const char *name, double alg_bytes)
 {
     const size_t csz = sizeof(cx<R>);
     const int L = rp.plan.L;
@@ -397,13 +416,14 @@ static int run_row(ndconv_processor *p, int kind /*0 fwd 1 inv 2 1d*/, RowParams
     else rp.nwork = rp.ntiles[0];
     int block = pick_block_threads((int64_t)rp.B * std::max(L / 4, 1));
     int64_t grid = std::min<int64_t>(rp.nwork, (int64_t)p->num_sms * 4 * kMaxGridMult);
-    if (kind == 0) return launch<RowFwdBody<R>, RowParams<R>>(p->stream, grid, block, smem, rp, &p->launches);
-    if (kind == 1) return launch<RowInvBody<R>, RowParams<R>>(p->stream, grid, block, smem, rp, &p->launches);
-    return launch<Row1DBody<R>, RowParams<R>>(p->stream, grid, block, smem, rp, &p->launches);
+    if (kind == 0) return launch<RowFwdBody<R>, RowParams<R>>(p->lc(), name, alg_bytes, grid, block, smem, rp);
+    if (kind == 1) return launch<RowInvBody<R>, RowParams<R>>(p->lc(), name, alg_bytes, grid, block, smem, rp);
+    return launch<Row1DBody<R>, RowParams<R>>(p->lc(), name, alg_bytes, grid, block, smem, rp);
 }
 
 template <class R>
-static int run_col(ndconv_processor *p, const FftPlan &pl, int axis, int mode, cx<R> *ws, const cx<R> *kspec, int64_t ntiles_total)
+static int run_col(ndconv_processor *p, const FftPlan &pl, int axis, int mode, cx<R> *ws, const cx<R> *kspec, int64_t ntiles_total,
+                   const char *name, double alg_bytes)
 {
     ColParams<R> cp; memset(&cp, 0, sizeof(cp));
     cp.ws = ws; cp.kspec = kspec; cp.F = pl.tl[axis].F; cp.mode = mode;
@@ -419,7 +439,7 @@ static int run_col(ndconv_processor *p, const FftPlan &pl, int axis, int mode, c
     size_t smem = 2 * (size_t)cp.F * W * sizeof(cx<R>) + 64;
     int block = pick_block_threads((int64_t)cp.F * W / 4);
     int64_t grid = std::min<int64_t>(cp.nwork, (int64_t)p->num_sms * 4 * kMaxGridMult);
-    return launch<ColBody<R>, ColParams<R>>(p->stream, grid, block, smem, cp, &p->launches);
+    return launch<ColBody<R>, ColParams<R>>(p->lc(), name, alg_bytes, grid, block, smem, cp);
 }
 
 // kernel spectrum (cached per processor): conv_fft::padding::kernel (src/conv_fft/padding.rs:78-111) + forward
@@ -482,8 +502,9 @@ static int get_kernel_spectrum(ndconv_processor *p, const ndconv_problem *pr, co
     rp.rows_per_tile = pl.rows_per_tile; rp.tile_elems = pl.tile_elems;
     st = fill_plan_dev<R>(p, pl.fl[N - 1], &rp.plan); if (st) return st;
     if (!pl.is_cx) { st = get_tw_r<R>(p, pl.tl[N - 1].F, &rp.twr); if (st) return st; }
-    st = run_row<R>(p, 0, rp, 0); if (st) return st;
-    for (int a = N - 2; a >= 0; a--) { st = run_col<R>(p, pl, a, 0, (cx<R> *)ent->buf.p, nullptr, 1); if (st) return st; }
+    const double kbytes = (double)pl.tile_elems * sizeof(cx<R>);
+    st = run_row<R>(p, 0, rp, 0, "kspec_row_fwd", kbytes); if (st) return st;
+    for (int a = N - 2; a >= 0; a--) { st = run_col<R>(p, pl, a, 0, (cx<R> *)ent->buf.p, nullptr, 1, "kspec_col_fwd", 2 * kbytes); if (st) return st; }
     // the staging buffers are reused by the next build: make sure this one has been consumed
     st = be_sync(p->stream); if (st) return st;
 
@@ -529,18 +550,23 @@ static int conv_fft_t(ndconv_processor *p, const ndconv_problem *pr, Geom &g, st
     st = fill_plan_dev<R>(p, pl.fl[N - 1], &rp.plan); if (st) return st;
     if (!pl.is_cx) { st = get_tw_r<R>(p, pl.tl[N - 1].F, &rp.twr); if (st) return st; }
 
+    // algorithmic bytes per pass: the un-inflated spectrum of the padded array, S complex elements
+    const double csz = (double)sizeof(cx<R>);
+    double S = pl.is_cx ? (double)g.P[N - 1] : (double)(g.P[N - 1] / 2 + 1), So = S;
+    for (int a = 0; a < N - 1; a++) { S *= (double)g.P[a]; So *= (double)g.O[a]; }
+    const double in_bytes = (double)g.es * (double)g.data_total, out_bytes = (double)g.es * (double)g.out_total;
     if (N == 1) {
-        st = run_row<R>(p, 2, rp, 1); if (st) return st;
+        st = run_row<R>(p, 2, rp, 1, "row1d_fwd_mul_inv", in_bytes + out_bytes); if (st) return st;
     } else {
         st = p->ws.reserve((size_t)pl.ntiles_total * pl.tile_elems * sizeof(cx<R>)); if (st) return st;
         rp.ws = (cx<R> *)p->ws.p;
-        st = run_row<R>(p, 0, rp, 0); if (st) return st;
-        for (int a = N - 2; a >= 1; a--) { st = run_col<R>(p, pl, a, 0, rp.ws, nullptr, pl.ntiles_total); if (st) return st; }
-        st = run_col<R>(p, pl, 0, 2, rp.ws, kspec, pl.ntiles_total); if (st) return st;
-        for (int a = 1; a <= N - 2; a++) { st = run_col<R>(p, pl, a, 1, rp.ws, nullptr, pl.ntiles_total); if (st) return st; }
+        st = run_row<R>(p, 0, rp, 0, "row_fwd_pad_r2c", in_bytes + S * csz); if (st) return st;
+        for (int a = N - 2; a >= 1; a--) { st = run_col<R>(p, pl, a, 0, rp.ws, nullptr, pl.ntiles_total, "col_fwd", 2 * S * csz); if (st) return st; }
+        st = run_col<R>(p, pl, 0, 2, rp.ws, kspec, pl.ntiles_total, "col_fwd_mul_inv", 2 * S * csz + (double)pl.tile_elems * csz); if (st) return st;
+        for (int a = 1; a <= N - 2; a++) { st = run_col<R>(p, pl, a, 1, rp.ws, nullptr, pl.ntiles_total, "col_inv", 2 * S * csz); if (st) return st; }
         int64_t out_rows = 1;
         for (int a = 0; a < N - 1; a++) out_rows *= g.O[a];
-        st = run_row<R>(p, 1, rp, out_rows); if (st) return st;
+        st = run_row<R>(p, 1, rp, out_rows, "row_inv_c2r_crop", So * csz + out_bytes); if (st) return st;
     }
     if (pr->memory == NDCONV_MEM_HOST) {
         st = be_d2h(out, dev_out, obytes, p->stream); if (st) return st;
@@ -679,6 +705,39 @@ int ndconv_processor_synchronize(ndconv_processor *p)
 }
 int64_t ndconv_processor_launch_count(const ndconv_processor *p) { return p ? p->launches : 0; }
 int64_t ndconv_processor_workspace_bytes(const ndconv_processor *p) { return p ? (int64_t)p->held() : 0; }
+
+int ndconv_processor_set_profiling(ndconv_processor *p, int enable)
+{
+    if (!p) { set_error("null processor"); return NDCONV_ERR_BAD_ARG; }
+    p->prof.on = enable != 0;
+    return NDCONV_OK;
+}
+
+int ndconv_processor_get_profile(ndconv_processor *p, int max_entries, char (*names)[64], double *total_ms, int64_t *launches, double *alg_bytes)
+{
+    if (!p) return 0;
+    int n = 0;
+#ifdef NDCONV_CUDA
+    set_device(p);
+    cudaStreamSynchronize(p->stream);
+    for (auto &r : p->prof.recs) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, r.a, r.b);
+        int i = 0;
+        for (; i < n; i++) if (!strncmp(names[i], r.name, 63)) break;
+        if (i == n) {
+            if (n >= max_entries) continue;
+            strncpy(names[n], r.name, 63); names[n][63] = 0; total_ms[n] = 0; launches[n] = 0; alg_bytes[n] = 0; n++;
+        }
+        total_ms[i] += ms; launches[i] += 1; alg_bytes[i] += r.bytes;
+        p->prof.pool.push_back(r.a); p->prof.pool.push_back(r.b);
+    }
+    p->prof.recs.clear();
+#else
+    (void)max_entries; (void)names; (void)total_ms; (void)launches; (void)alg_bytes;
+#endif
+    return n;
+}
 
 static int with_processor(ndconv_processor *p, const ndconv_problem *pr, void *out, int (*fn)(ndconv_processor *, const ndconv_problem *, void *))
 {
