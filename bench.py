@@ -186,7 +186,11 @@ def run_gpu(args, w, rank, world, local_rank):
         xv[r:r + step_rows] = rng.random((min(step_rows, rows - r), n1), dtype=np.float32)
     x_dev = x_pin.to(dev, non_blocking=False)
     proc = pkg.get_fft_processor(local_rank, lib)
-    stream = torch.cuda.current_stream(dev)
+    # a dedicated (non-default) stream: kernels and the timing events live on the same stream; the legacy default
+    # stream's handle is 0, which the C ABI reads as "use the processor's own stream"
+    stream = torch.cuda.Stream(dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     proc.set_stream(stream.cuda_stream)
     oshape = pkg.conv_device("ndconv_conv_fft", proc, x_dev.data_ptr(), (rows, n1), (n1, 1), np.float32, kwd, mode, pmode, None, explicit=explicit)
     assert oshape[0] == out_rows, (oshape, out_rows)

@@ -16,6 +16,7 @@
 #include "host_logic.h"
 #include "kernels_direct.h"
 #include "kernels_fft.h"
+#include "kernels_fft_opt.cuh"
 
 #ifdef NDCONV_CUDA
 #include <cuda_runtime.h>
@@ -69,6 +70,18 @@ static int launch(const LaunchCtx &lc, const char *name, double alg_bytes, int64
     const bool prof = lc.prof && lc.prof->on;
     if (prof) { rec.name = name; rec.bytes = alg_bytes; rec.a = lc.prof->get(); rec.b = lc.prof->get(); CU_CHECK(cudaEventRecord(rec.a, lc.st)); }
     kentry<Body, Params><<<(unsigned)grid, block, smem, lc.st>>>(p);
+    CU_CHECK(cudaGetLastError());
+    if (prof) { CU_CHECK(cudaEventRecord(rec.b, lc.st)); lc.prof->recs.push_back(rec); }
+    if (lc.counter) (*lc.counter)++;
+    return NDCONV_OK;
+}
+// launch of a plain __global__ kernel (the sm_100a fast path) with the same counting / profiling
+template <class F> static int launch_raw(const LaunchCtx &lc, const char *name, double alg_bytes, F &&do_launch)
+{
+    ProfRec rec;
+    const bool prof = lc.prof && lc.prof->on;
+    if (prof) { rec.name = name; rec.bytes = alg_bytes; rec.a = lc.prof->get(); rec.b = lc.prof->get(); CU_CHECK(cudaEventRecord(rec.a, lc.st)); }
+    do_launch();
     CU_CHECK(cudaGetLastError());
     if (prof) { CU_CHECK(cudaEventRecord(rec.b, lc.st)); lc.prof->recs.push_back(rec); }
     if (lc.counter) (*lc.counter)++;
@@ -132,6 +145,7 @@ struct DevBuf {
 struct KSpecEntry {
     std::vector<unsigned char> key;
     DevBuf buf;
+    DevBuf pair;     // paired layout for the sm_100a 2-D fast path
     uint64_t last_use = 0;
 };
 
@@ -150,7 +164,7 @@ struct ndconv_processor {
     size_t held() const
     {
         size_t s = ws.cap + in_stage.cap + out_stage.cap + meta.cap + kb_stage.cap + kmeta.cap;
-        for (auto &k : kspecs) s += k->buf.cap;
+        for (auto &k : kspecs) s += k->buf.cap + k->pair.cap;
         return s;
     }
 };
@@ -350,18 +364,39 @@ static int cap_col_axis(bool is_dbl) { return is_dbl ? 512 : 1024; }
 struct FftPlan {
     int N = 0;
     bool is_cx = false;
+    bool opt2d = false;           // sm_100a fast path: 2-D real f32, tile 1024 x 2048 (kernels_fft_opt.cuh)
     AxisTiling tl[NDC_MAX_DIM];
     FftLen fl[NDC_MAX_DIM];       // complex transform per axis (last axis: F/2 for real input)
     int H = 0, Hp = 0;
     int64_t rows_per_tile = 1, tile_elems = 0, ntiles_total = 1;
 };
 
+static bool opt2d_eligible(const Geom &g)
+{
+#ifdef NDCONV_CUDA
+    static const bool disabled = getenv("NDCONV_DISABLE_OPT") != nullptr;
+    if (disabled) return false;
+    return g.ndim == 2 && g.dtype == NDCONV_F32 && g.P[0] >= 600 && g.P[1] >= 1200 && g.Kd[0] <= 512 && g.Kd[1] <= 1024;
+#else
+    (void)g;
+    return false;
+#endif
+}
+
 static int make_plan(const Geom &g, FftPlan *pl)
 {
     const int N = g.ndim;
     const bool is_cx = dtype_is_complex(g.dtype), is_dbl = (g.dtype == NDCONV_F64 || g.dtype == NDCONV_C64);
     pl->N = N; pl->is_cx = is_cx;
+    pl->opt2d = opt2d_eligible(g);
     for (int a = 0; a < N; a++) {
+        if (pl->opt2d) {
+            const int F = a == 0 ? 1024 : 2048;
+            pl->tl[a].F = F; pl->tl[a].V = F - (int)g.Kd[a] + 1;
+            pl->tl[a].ntiles = (int)((g.P[a] - g.Kd[a] + 1 + pl->tl[a].V - 1) / pl->tl[a].V);
+            if (!factor_radices(a == 0 ? F : F / 2, &pl->fl[a])) return NDCONV_ERR_INTERNAL;
+            continue;
+        }
         const bool last = (a == N - 1);
         const bool real_axis = last && !is_cx;
         int cap = last ? cap_last_axis(is_cx, is_dbl) : cap_col_axis(is_dbl);
@@ -444,7 +479,7 @@ static int run_col(ndconv_processor *p, const FftPlan &pl, int axis, int mode, c
 
 // kernel spectrum (cached per processor): conv_fft::padding::kernel (src/conv_fft/padding.rs:78-111) + forward
 template <class R>
-static int get_kernel_spectrum(ndconv_processor *p, const ndconv_problem *pr, const Geom &g, const FftPlan &pl, const cx<R> **out)
+static int get_kernel_spectrum(ndconv_processor *p, const ndconv_problem *pr, const Geom &g, const FftPlan &pl, const cx<R> **out, KSpecEntry **out_entry = nullptr)
 {
     const int N = g.ndim;
     std::vector<unsigned char> kpacked((size_t)g.kernel_total * g.es);
@@ -457,7 +492,7 @@ static int get_kernel_spectrum(ndconv_processor *p, const ndconv_problem *pr, co
     for (int a = 0; a < N; a++) { int64_t v[3] = {g.k[a], g.d[a], (int64_t)pl.tl[a].F}; push(v, sizeof(v)); }
     push(kpacked.data(), kpacked.size());
     p->tick++;
-    for (auto &e : p->kspecs) if (e->key == key) { e->last_use = p->tick; *out = (const cx<R> *)e->buf.p; return NDCONV_OK; }
+    for (auto &e : p->kspecs) if (e->key == key) { e->last_use = p->tick; *out = (const cx<R> *)e->buf.p; if (out_entry) *out_entry = e.get(); return NDCONV_OK; }
 
     // dense dilated (and, for no_reverse, flipped) kernel of extent Kd, pre-scaled by 1/prod(F) (the reference divides
     // after the inverse transform: real.rs:278-279, complex.rs:141-142)
@@ -512,12 +547,71 @@ static int get_kernel_spectrum(ndconv_processor *p, const ndconv_problem *pr, co
         size_t victim = 0;
         for (size_t i = 1; i < p->kspecs.size(); i++) if (p->kspecs[i]->last_use < p->kspecs[victim]->last_use) victim = i;
         p->kspecs[victim]->buf.release();
+        p->kspecs[victim]->pair.release();
         p->kspecs.erase(p->kspecs.begin() + victim);
     }
     *out = (const cx<R> *)ent->buf.p;
+    if (out_entry) *out_entry = ent.get();
     p->kspecs.push_back(std::move(ent));
     return NDCONV_OK;
 }
+
+#ifdef NDCONV_CUDA
+// sm_100a fast path: 2-D real f32, tiles 1024 x 2048 (kernels_fft_opt.cuh)
+static int conv_fft_opt2d(ndconv_processor *p, const ndconv_problem *pr, const Geom &g, const FftPlan &pl, const MetaLayout &ml,
+                          const void *dev_x, void *dev_out, KSpecEntry *ent)
+{
+    using namespace ndc::opt;
+    int st;
+    if (!ent->pair.p) {
+        st = ent->pair.reserve((size_t)kF0 * kKP * sizeof(float4)); if (st) return st;
+        KpairParams kp; kp.kspec = (const cx<float> *)ent->buf.p; kp.kpair = (float *)ent->pair.p; kp.F0 = kF0; kp.L = kL; kp.Hp = pl.Hp; kp.KP = kKP;
+        st = launch<KpairBody, KpairParams>(p->lc(), "kspec_pair_repack", (double)kF0 * kKP * 16, p->num_sms * 4, 256, 0, kp); if (st) return st;
+    }
+    const int64_t tile_elems = (int64_t)kF0 * kL;
+    st = p->ws.reserve((size_t)pl.ntiles_total * tile_elems * sizeof(cf)); if (st) return st;
+    const cx<float> *tw = nullptr, *twr = nullptr;
+    st = get_tw_c<float>(p, kL, &tw); if (st) return st;
+    st = get_tw_r<float>(p, kF1, &twr); if (st) return st;
+
+    RowOptParams rp; memset(&rp, 0, sizeof(rp));
+    for (int a = 0; a < 2; a++) {
+        rp.n[a] = g.n[a]; rp.xstr[a] = g.xstr[a]; rp.P[a] = g.P[a]; rp.pf[a] = g.pf[a];
+        rp.map[a] = (const int32_t *)((const unsigned char *)p->meta.p + ml.map_off[a]);
+        rp.V[a] = pl.tl[a].V; rp.ntiles[a] = pl.tl[a].ntiles; rp.Kd[a] = (int)g.Kd[a]; rp.s[a] = g.s[a]; rp.O[a] = g.O[a];
+        rp.cfront[a] = pr->border[a][0].type == NDCONV_BORDER_CONST ? *(const float *)pr->border[a][0].value : 0.f;
+        rp.cback[a] = pr->border[a][1].type == NDCONV_BORDER_CONST ? *(const float *)pr->border[a][1].value : 0.f;
+    }
+    rp.x = (const float *)dev_x; rp.out = (float *)dev_out; rp.ws = (cf *)p->ws.p; rp.tw = tw;
+
+    static bool attr_set = false;
+    if (!attr_set) { CU_CHECK(cudaFuncSetAttribute(col_pair_fmi, cudaFuncAttributeMaxDynamicSharedMemorySize, kColSmem)); attr_set = true; }
+
+    const double csz = 8.0;
+    double S = (double)(g.P[1] / 2 + 1) * (double)g.P[0], So = (double)(g.P[1] / 2 + 1) * (double)g.O[0];
+    const double in_bytes = 4.0 * (double)g.data_total, out_bytes = 4.0 * (double)g.out_total;
+    const stream_t stm = p->stream;
+
+    rp.nwork = pl.ntiles_total * kF0;
+    {
+        const int grid = (int)std::min<int64_t>((rp.nwork + 3) / 4, (int64_t)p->num_sms * 4 * 8);
+        st = launch_raw(p->lc(), "row_fwd_pad_r2c", in_bytes + S * csz, [&] { row_fwd_packed<<<grid, 128, 0, stm>>>(rp); }); if (st) return st;
+    }
+    {
+        ColOptParams cp; cp.ws = (cf *)p->ws.p; cp.kpair = (const float4 *)ent->pair.p; cp.tw = tw; cp.twr = twr;
+        cp.ntiles_total = pl.ntiles_total; cp.nwork = pl.ntiles_total * (kL / 8);
+        const int grid = (int)std::min<int64_t>(cp.nwork, (int64_t)p->num_sms * 2);
+        st = launch_raw(p->lc(), "col_fwd_mul_inv", 2 * S * csz + (double)kF0 * kKP * 16,
+                        [&] { col_pair_fmi<<<grid, 256, kColSmem, stm>>>(cp); }); if (st) return st;
+    }
+    rp.nwork = g.O[0] * pl.tl[1].ntiles;
+    {
+        const int grid = (int)std::min<int64_t>((rp.nwork + 3) / 4, (int64_t)p->num_sms * 4 * 8);
+        st = launch_raw(p->lc(), "row_inv_c2r_crop", So * csz + out_bytes, [&] { row_inv_packed<<<grid, 128, 0, stm>>>(rp); }); if (st) return st;
+    }
+    return NDCONV_OK;
+}
+#endif
 
 template <class R>
 static int conv_fft_t(ndconv_processor *p, const ndconv_problem *pr, Geom &g, std::vector<int32_t> *maps, void *out)
@@ -530,11 +624,24 @@ static int conv_fft_t(ndconv_processor *p, const ndconv_problem *pr, Geom &g, st
     MetaLayout ml;
     st = upload_meta(p, p->meta, g, maps, nullptr, &ml); if (st) return st;
     const cx<R> *kspec = nullptr;
-    st = get_kernel_spectrum<R>(p, pr, g, pl, &kspec); if (st) return st;
+    KSpecEntry *kent = nullptr;
+    st = get_kernel_spectrum<R>(p, pr, g, pl, &kspec, &kent); if (st) return st;
 
     size_t obytes = (size_t)g.out_total * g.es;
     void *dev_out = out;
     if (pr->memory == NDCONV_MEM_HOST) { st = p->out_stage.reserve(obytes); if (st) return st; dev_out = p->out_stage.p; }
+#ifdef NDCONV_CUDA
+    if (pl.opt2d) {
+        if constexpr (sizeof(R) == 4) {
+            st = conv_fft_opt2d(p, pr, g, pl, ml, dev_x, dev_out, kent); if (st) return st;
+            if (pr->memory == NDCONV_MEM_HOST) {
+                st = be_d2h(out, dev_out, obytes, p->stream); if (st) return st;
+                st = be_sync(p->stream); if (st) return st;
+            }
+            return NDCONV_OK;
+        }
+    }
+#endif
 
     RowParams<R> rp; memset(&rp, 0, sizeof(rp));
     rp.ndim = N; rp.is_cx = pl.is_cx ? 1 : 0;
@@ -683,7 +790,7 @@ int ndconv_processor_destroy(ndconv_processor *p)
     p->ws.release(); p->in_stage.release(); p->out_stage.release(); p->meta.release(); p->kb_stage.release(); p->kmeta.release();
     for (auto &kv : p->tw_c) be_free(kv.second);
     for (auto &kv : p->tw_r) be_free(kv.second);
-    for (auto &k : p->kspecs) k->buf.release();
+    for (auto &k : p->kspecs) { k->buf.release(); k->pair.release(); }
 #ifdef NDCONV_CUDA
     if (p->own_stream) cudaStreamDestroy(p->own_stream);
 #endif

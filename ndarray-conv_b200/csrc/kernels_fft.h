@@ -48,6 +48,50 @@ template <class R> HD void dft8(cx<R> *v, bool inv)
     o[1] = cmul(o[1], w1); o[2] = mul_neg_i(o[2], inv); o[3] = cmul(o[3], w3);
     for (int q = 0; q < 4; q++) { v[q] = cadd(e[q], o[q]); v[q + 4] = csub(e[q], o[q]); }
 }
+// cos / sin (2 pi m / 32): the in-register twiddles of the composite radix-16 / radix-32 butterflies
+HD constexpr double w32_cos(int m)
+{
+    constexpr double t[32] = {1.0, 0.9807852804032304, 0.9238795325112867, 0.8314696123025452, 0.7071067811865476, 0.5555702330196023, 0.38268343236508984, 0.19509032201612833, 6.123233995736766e-17, -0.1950903220161282, -0.3826834323650897, -0.555570233019602, -0.7071067811865475, -0.8314696123025453, -0.9238795325112867, -0.9807852804032304, -1.0, -0.9807852804032304, -0.9238795325112868, -0.8314696123025455, -0.7071067811865477, -0.5555702330196022, -0.38268343236509034, -0.19509032201612866, -1.8369701987210297e-16, 0.1950903220161283, 0.38268343236509, 0.5555702330196018, 0.7071067811865474, 0.8314696123025452, 0.9238795325112865, 0.9807852804032303};
+    return t[m & 31];
+}
+HD constexpr double w32_sin(int m)
+{
+    constexpr double t[32] = {0.0, 0.19509032201612825, 0.3826834323650898, 0.5555702330196022, 0.7071067811865475, 0.8314696123025452, 0.9238795325112867, 0.9807852804032304, 1.0, 0.9807852804032304, 0.9238795325112867, 0.8314696123025455, 0.7071067811865476, 0.5555702330196022, 0.3826834323650899, 0.1950903220161286, 1.2246467991473532e-16, -0.19509032201612836, -0.38268343236508967, -0.555570233019602, -0.7071067811865475, -0.8314696123025452, -0.9238795325112865, -0.9807852804032303, -1.0, -0.9807852804032304, -0.9238795325112866, -0.8314696123025455, -0.7071067811865477, -0.5555702330196022, -0.3826834323650904, -0.19509032201612872};
+    return t[m & 31];
+}
+// Cooley-Tukey N = N1*N2 in registers: n = N2*n1 + n2, k = k1 + N1*k2.  Natural order in, natural order out.
+template <class R, int N1, int N2, class DFT1, class DFT2> HD void dft_ct(cx<R> *v, bool inv, DFT1 d1, DFT2 d2)
+{
+    constexpr int N = N1 * N2;
+    cx<R> a[N2][N1];
+#pragma unroll
+    for (int n2 = 0; n2 < N2; n2++) {
+#pragma unroll
+        for (int n1 = 0; n1 < N1; n1++) a[n2][n1] = v[N2 * n1 + n2];
+        d1(a[n2], inv);                                   // a[n2][k1]
+    }
+#pragma unroll
+    for (int k1 = 0; k1 < N1; k1++) {
+        cx<R> b[N2];
+#pragma unroll
+        for (int n2 = 0; n2 < N2; n2++) {
+            const int m = (n2 * k1 * (32 / N)) & 31;      // W_N^{n2 k1} = W_32^{n2 k1 32/N}
+            if (m == 0) b[n2] = a[n2][k1];
+            else {
+                const cx<R> w = cx<R>{(R)w32_cos(m), (R)(inv ? w32_sin(m) : -w32_sin(m))};
+                b[n2] = cmul(a[n2][k1], w);
+            }
+        }
+        d2(b, inv);                                       // b[k2]
+#pragma unroll
+        for (int k2 = 0; k2 < N2; k2++) v[k1 + N1 * k2] = b[k2];
+    }
+}
+template <class R> struct Dft4Fn { HD void operator()(cx<R> *v, bool inv) const { dft4(v, inv); } };
+template <class R> struct Dft8Fn { HD void operator()(cx<R> *v, bool inv) const { dft8(v, inv); } };
+template <class R> HD void dft16(cx<R> *v, bool inv) { dft_ct<R, 4, 4>(v, inv, Dft4Fn<R>(), Dft4Fn<R>()); }
+template <class R> HD void dft32(cx<R> *v, bool inv) { dft_ct<R, 4, 8>(v, inv, Dft4Fn<R>(), Dft8Fn<R>()); }
+
 // odd prime radices: O(R^2) with exact constants
 template <class R, int RDX> HD void dft_odd(cx<R> *v, bool inv)
 {
@@ -84,6 +128,8 @@ template <class R, int RDX> HD void dft(cx<R> *v, bool inv)
     if constexpr (RDX == 2) dft2(v);
     else if constexpr (RDX == 4) dft4(v, inv);
     else if constexpr (RDX == 8) dft8(v, inv);
+    else if constexpr (RDX == 16) dft16(v, inv);
+    else if constexpr (RDX == 32) dft32(v, inv);
     else dft_odd<R, RDX>(v, inv);
 }
 
@@ -131,6 +177,8 @@ HD cx<R> *fft_smem(const BlockCtx &c, cx<R> *a, cx<R> *b, const FftPlanDev<R> &p
         case 4: stockham_pass_r<R, 4>(c, in, out, pl.L, Ns, pl.tw, inv, nbatch, estride, bstride, batch_fast); break;
         case 5: stockham_pass_r<R, 5>(c, in, out, pl.L, Ns, pl.tw, inv, nbatch, estride, bstride, batch_fast); break;
         case 7: stockham_pass_r<R, 7>(c, in, out, pl.L, Ns, pl.tw, inv, nbatch, estride, bstride, batch_fast); break;
+        case 16: stockham_pass_r<R, 16>(c, in, out, pl.L, Ns, pl.tw, inv, nbatch, estride, bstride, batch_fast); break;
+        case 32: stockham_pass_r<R, 32>(c, in, out, pl.L, Ns, pl.tw, inv, nbatch, estride, bstride, batch_fast); break;
         default: stockham_pass_r<R, 8>(c, in, out, pl.L, Ns, pl.tw, inv, nbatch, estride, bstride, batch_fast); break;
         }
         Ns *= r;

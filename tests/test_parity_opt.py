@@ -1,0 +1,59 @@
+"""sm_100a fast path (kernels_fft_opt.cuh: 2-D real f32, 1024 x 2048 overlap-save tiles) against the CPU oracle.
+Device-only kernels (warp shuffles): these tests need a B200."""
+import numpy as np
+import pytest
+
+from test_parity_small import fft_tol, mode_from_spec, padding_from_spec
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    # shape, kernel, dilation, mode, padding, reverse
+    ((700, 1500), (5, 9), 1, "same", "zeros", True),
+    ((1300, 2600), (5, 9), 1, "full", "reflect", True),
+    ((1300, 2600), (4, 6), 2, "same", ("custom", ["circular", ("const", 1.5)]), False),
+    ((2100, 4200), (7, 3), 1, ("custom", [3, 5], [2, 3]), "replicate", True),
+    ((1025, 2049), (63, 63), 1, "valid", "zeros", True),
+    ((900, 5000), (3, 31), 3, ("explicit", [[0, 7], [40, 2]], [1, 1]), ("explicit", [["zeros", "reflect"], ["circular", "replicate"]]), True),
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[str(c[:2]) for c in CASES])
+def test_opt2d_vs_oracle(pkg, cuda_lib, oracle, case):
+    shape, ks, dil, mode, padding, rev = case
+    rng = np.random.default_rng(42)
+    x = rng.random(shape, dtype=np.float32) - 0.25
+    k = rng.random(ks, dtype=np.float32) - 0.5
+    kw = pkg.with_dilation(k, dil)
+    if not rev:
+        kw = kw.no_reverse()
+    proc = pkg.get_fft_processor(0, cuda_lib)
+    got = pkg.conv_fft_with_processor(x, kw, mode_from_spec(pkg, mode), padding_from_spec(pkg, padding), proc)
+    got2 = pkg.conv_fft_with_processor(x, kw, mode_from_spec(pkg, mode), padding_from_spec(pkg, padding), proc)   # cached kernel spectrum
+    ref = oracle.conv_f64_truth(x, k, mode, padding, dil, rev)
+    assert got.shape == ref.shape
+    tol = fft_tol(np.float32, 1024 * 2048, ref)
+    assert np.max(np.abs(got - ref)) <= tol, (np.max(np.abs(got - ref)), tol)
+    assert np.array_equal(got, got2)
+    proc.close()
+
+
+def test_opt2d_matches_generic_path(pkg, cuda_lib):
+    """same input through the fast path and (NDCONV_DISABLE_OPT=1, subprocess) the generic path"""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import importlib,numpy as np,sys; sys.path.insert(0,'.');"
+        "pkg=importlib.import_module('ndarray-conv_b200');"
+        "rng=np.random.default_rng(3); x=rng.random((1200,2500),dtype=np.float32); k=rng.random((9,11),dtype=np.float32);"
+        "y=pkg.conv_fft(x,k,pkg.ConvMode.Full,pkg.PaddingMode.Reflect); np.save(sys.argv[1],y)"
+    )
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for tag, env in (("opt", {}), ("gen", {"NDCONV_DISABLE_OPT": "1"})):
+        path = f"/tmp/ndconv_{tag}.npy"
+        subprocess.run([sys.executable, "-c", code, path], check=True, cwd=root, env={**os.environ, **env})
+        outs.append(np.load(path))
+    scale = float(np.max(np.abs(outs[1])))
+    assert np.max(np.abs(outs[0] - outs[1])) <= 8 * np.finfo(np.float32).eps * np.log2(1024 * 2048) * scale
