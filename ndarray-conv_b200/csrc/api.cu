@@ -564,9 +564,9 @@ static int conv_fft_opt2d(ndconv_processor *p, const ndconv_problem *pr, const G
     using namespace ndc::opt;
     int st;
     if (!ent->pair.p) {
-        st = ent->pair.reserve((size_t)kF0 * kKP * sizeof(float4)); if (st) return st;
-        KpairParams kp; kp.kspec = (const cx<float> *)ent->buf.p; kp.kpair = (float *)ent->pair.p; kp.F0 = kF0; kp.L = kL; kp.Hp = pl.Hp; kp.KP = kKP;
-        st = launch<KpairBody, KpairParams>(p->lc(), "kspec_pair_repack", (double)kF0 * kKP * 16, p->num_sms * 4, 256, 0, kp); if (st) return st;
+        st = ent->pair.reserve((size_t)kF0 * kKphysPitch * sizeof(cf)); if (st) return st;
+        KphysParams kp; kp.kspec = (const cx<float> *)ent->buf.p; kp.kphys = (cx<float> *)ent->pair.p; kp.F0 = kF0; kp.L = kL; kp.Hp = pl.Hp; kp.pitch = kKphysPitch;
+        st = launch<KphysBody, KphysParams>(p->lc(), "kspec_phys_repack", (double)kF0 * kKphysPitch * 16, p->num_sms * 4, 256, 0, kp); if (st) return st;
     }
     const int64_t tile_elems = (int64_t)kF0 * kL;
     st = p->ws.reserve((size_t)pl.ntiles_total * tile_elems * sizeof(cf)); if (st) return st;
@@ -582,10 +582,10 @@ static int conv_fft_opt2d(ndconv_processor *p, const ndconv_problem *pr, const G
         rp.cfront[a] = pr->border[a][0].type == NDCONV_BORDER_CONST ? *(const float *)pr->border[a][0].value : 0.f;
         rp.cback[a] = pr->border[a][1].type == NDCONV_BORDER_CONST ? *(const float *)pr->border[a][1].value : 0.f;
     }
-    rp.x = (const float *)dev_x; rp.out = (float *)dev_out; rp.ws = (cf *)p->ws.p; rp.tw = tw;
+    rp.x = (const float *)dev_x; rp.out = (float *)dev_out; rp.ws = (cf *)p->ws.p; rp.tw = tw; rp.twr = twr;
 
     static bool attr_set = false;
-    if (!attr_set) { CU_CHECK(cudaFuncSetAttribute(col_pair_fmi, cudaFuncAttributeMaxDynamicSharedMemorySize, kColSmem)); attr_set = true; }
+    if (!attr_set) { CU_CHECK(cudaFuncSetAttribute(col_fmi, cudaFuncAttributeMaxDynamicSharedMemorySize, kColSmem)); attr_set = true; }
 
     const double csz = 8.0;
     double S = (double)(g.P[1] / 2 + 1) * (double)g.P[0], So = (double)(g.P[1] / 2 + 1) * (double)g.O[0];
@@ -598,11 +598,11 @@ static int conv_fft_opt2d(ndconv_processor *p, const ndconv_problem *pr, const G
         st = launch_raw(p->lc(), "row_fwd_pad_r2c", in_bytes + S * csz, [&] { row_fwd_packed<<<grid, 128, 0, stm>>>(rp); }); if (st) return st;
     }
     {
-        ColOptParams cp; cp.ws = (cf *)p->ws.p; cp.kpair = (const float4 *)ent->pair.p; cp.tw = tw; cp.twr = twr;
+        ColOptParams cp; cp.ws = (cf *)p->ws.p; cp.kphys = (const cf *)ent->pair.p; cp.tw = tw;
         cp.ntiles_total = pl.ntiles_total; cp.nwork = pl.ntiles_total * (kL / 8);
         const int grid = (int)std::min<int64_t>(cp.nwork, (int64_t)p->num_sms * 2);
-        st = launch_raw(p->lc(), "col_fwd_mul_inv", 2 * S * csz + (double)kF0 * kKP * 16,
-                        [&] { col_pair_fmi<<<grid, 256, kColSmem, stm>>>(cp); }); if (st) return st;
+        st = launch_raw(p->lc(), "col_fwd_mul_inv", 2 * S * csz + (double)kF0 * kKphysPitch * 8,
+                        [&] { col_fmi<<<grid, 256, kColSmem, stm>>>(cp); }); if (st) return st;
     }
     rp.nwork = g.O[0] * pl.tl[1].ntiles;
     {

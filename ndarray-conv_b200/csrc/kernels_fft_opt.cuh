@@ -1,18 +1,19 @@
 // kernels_fft_opt.cuh -- sm_100a fast path of the 2-D real conv_fft pipeline (device only).
 //
 // Tile = F0 x F1 = 1024 x 2048 real samples (overlap-save in both axes).  A row of 2048 reals is packed as
-// L = 1024 complex z[j] = x[2j] + i x[2j+1]; the R2C post-processing and the C2R pre-processing of the
-// half-length trick are NOT done per row: they are folded, together with the multiply by the cached kernel
-// spectrum, into the column kernel, where column k and column L-k of the packed spectrum sit side by side.
+// L = 1024 complex z[j] = x[2j] + i x[2j+1] (half-length real FFT).
 //
 //   row_fwd_packed   one warp per row: border-mapped (or plain vector) loads straight into registers, radix-32 x
-//                    radix-32 Stockham with one warp-private shared-memory transpose, warp-shuffle pairing, 16-byte
-//                    stores in the PAIRED layout: slot k in [0,512) holds (Z[k], Z[L-k]); slot 0 holds (Z[0], Z[L/2]).
-//   col_pair_fmi     256 threads per 1024 x 8-column tile (= 4 slots): radix-32 x radix-32 forward along the strided
-//                    axis, X = E + w^k O, Y = X .* K, re-packing, radix-32 x radix-32 inverse, in place.
-//   row_inv_packed   one warp per (output row, tile): paired loads, inverse radix-32 x radix-32, crop [Kd-1, F) and
-//                    stride decimation fused into the (vector) store.
-//   kpair_repack     kernel spectrum [F0][L+1] (generic path, cached) -> Kpair[q][slot] = (K[q][k], K[-q][L-k]).
+//                    radix-32 Stockham with one warp-private shared-memory transpose; Z[L-k] is fetched from its owner
+//                    lane by warp shuffle, the R2C post-processing X[k] = E + w^k O is done in registers, and the row
+//                    is stored with 16-byte stores in the PAIRED layout: slot k in [1,512) holds (X[k], X[L-k]);
+//                    slot 0 holds ((X[0], X[L]) packed as re/im -- both are real --, X[L/2]).
+//   col_fmi          256 threads per 1024 x 8-column tile: radix-32 x radix-32 forward along the strided axis, multiply by
+//                    the cached kernel spectrum (same physical layout), radix-32 x radix-32 inverse, in place.  Physical
+//                    column 0 carries two real sequences (DC / Nyquist); it is separated through its q <-> -q mirror.
+//   row_inv_packed   one warp per (output row, tile): paired loads, C2R pre-processing in registers, shuffle, inverse
+//                    radix-32 x radix-32, crop [Kd-1, F) and stride decimation fused into the (vector) store.
+//   kphys_repack     kernel spectrum [F0][L+1] (generic path, cached) -> the physical column order above.
 //
 // Reference stages replaced: conv_fft/padding.rs:30-62, processor/real.rs:105-154, mod.rs:268, real.rs:233-280,
 // mod.rs:282-289 (see kernels_fft.h for the stage-by-stage citations).
@@ -45,6 +46,7 @@ struct RowOptParams {
     float *out;
     cf *ws;                 // [tile][kF0][kL] paired layout
     const cf *tw;           // exp(-2 pi i j / 1024), j < 1024
+    const cf *twr;          // exp(-2 pi i k / 2048), k <= 512
     int64_t nwork;
 };
 
@@ -58,9 +60,11 @@ __device__ __forceinline__ void load_tw_table(cf *s_tw, const cf *tw, int tid, i
 __global__ void __launch_bounds__(128, 4) row_fwd_packed(const __grid_constant__ RowOptParams p)
 {
     __shared__ cf s_tw[1024];
+    __shared__ cf s_twr[512];
     __shared__ cf s_buf[4][32 * 33];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     load_tw_table(s_tw, p.tw, threadIdx.x, blockDim.x);
+    for (int idx = threadIdx.x; idx < 512; idx += blockDim.x) s_twr[idx] = p.twr[idx];
     __syncthreads();
     cf *sb = s_buf[warp];
     const int src_lane = (32 - lane) & 31;
@@ -128,13 +132,24 @@ __global__ void __launch_bounds__(128, 4) row_fwd_packed(const __grid_constant__
         for (int i = 0; i < 32; i++) v[i] = sb[lane * 33 + i];
         __syncwarp();
         dft32<float>(v, false);                                  // over t -> k2: v[k2] = Z[lane + 32 k2]
-        // pair (Z[k], Z[L-k]): the partner lives in lane (32-lane)&31, register 31-k2 (lane 0: register 32-k2; k = 0 pairs with L/2)
+        // Z[L-k] lives in lane (32-lane)&31, register 31-k2 (lane 0: register 32-k2; k = 0 pairs with L/2).
+        // R2C post-processing: E = (Z[k] + conj Z[L-k])/2, O = -i (Z[k] - conj Z[L-k])/2, X[k] = E + w^k O, X[L-k] = conj(E - w^k O)
 #pragma unroll
         for (int k2 = 0; k2 < 16; k2++) {
             float px = __shfl_sync(0xffffffffu, v[31 - k2].re, src_lane);
             float py = __shfl_sync(0xffffffffu, v[31 - k2].im, src_lane);
             if (lane == 0) { const cf o = (k2 == 0) ? v[16] : v[(32 - k2) & 31]; px = o.re; py = o.im; }
-            dst[lane + 32 * k2] = make_float4(v[k2].re, v[k2].im, px, py);
+            const cf zk = v[k2];
+            float4 o4;
+            if (lane == 0 && k2 == 0) {
+                o4 = make_float4(zk.re + zk.im, zk.re - zk.im, px, -py);          // (X[0], X[L]) packed ; X[L/2] = conj Z[L/2]
+            } else {
+                const cf E = cf{0.5f * (zk.re + px), 0.5f * (zk.im - py)};
+                const cf O = cf{0.5f * (zk.im + py), -0.5f * (zk.re - px)};
+                const cf t = cmul(s_twr[lane + 32 * k2], O);
+                o4 = make_float4(E.re + t.re, E.im + t.im, E.re - t.re, -(E.im - t.im));
+            }
+            dst[lane + 32 * k2] = o4;
         }
     }
 }
@@ -143,9 +158,11 @@ __global__ void __launch_bounds__(128, 4) row_fwd_packed(const __grid_constant__
 __global__ void __launch_bounds__(128, 4) row_inv_packed(const __grid_constant__ RowOptParams p)
 {
     __shared__ cf s_tw[1024];
+    __shared__ cf s_twr[512];
     __shared__ cf s_buf[4][32 * 33];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     load_tw_table(s_tw, p.tw, threadIdx.x, blockDim.x);
+    for (int idx = threadIdx.x; idx < 512; idx += blockDim.x) s_twr[idx] = p.twr[idx];
     __syncthreads();
     cf *sb = s_buf[warp];
     const int src_lane = (32 - lane) & 31;
@@ -162,8 +179,17 @@ __global__ void __launch_bounds__(128, 4) row_inv_packed(const __grid_constant__
 #pragma unroll
         for (int k2 = 0; k2 < 16; k2++) {
             const float4 t = src[lane + 32 * k2];
-            v[k2] = cf{t.x, t.y};
-            b[k2] = cf{t.z, t.w};
+            // C2R pre-processing (x2): Z[k] = E + i O, Z[L-k] = conj(E) + i conj(O), E = Y[k] + conj Y[L-k], O = conj(w^k) (Y[k] - conj Y[L-k])
+            if (lane == 0 && k2 == 0) {
+                v[0] = cf{t.x + t.y, t.x - t.y};                                   // slot 0 = ((Y[0], Y[L]) packed, Y[L/2])
+                b[0] = cf{2.f * t.z, -2.f * t.w};                                  // Z[L/2] = 2 conj Y[L/2]
+            } else {
+                const cf E = cf{t.x + t.z, t.y - t.w};
+                const cf D = cf{t.x - t.z, t.y + t.w};
+                const cf O = cmulc(D, s_twr[lane + 32 * k2]);
+                v[k2] = cf{E.re - O.im, E.im + O.re};
+                b[k2] = cf{E.re + O.im, -E.im + O.re};
+            }
         }
         // v[j'] for j' >= 16 is Zy[lane + 32 j'] = the partner half loaded by lane (32-lane)&31 at index 31-j'
 #pragma unroll
@@ -219,11 +245,12 @@ __global__ void __launch_bounds__(128, 4) row_inv_packed(const __grid_constant__
 }
 
 // ---- column forward * K * inverse ----------------------------------------------------------------------
+constexpr int kKphysPitch = kL + 8;      // kernel spectrum in physical column order, [kF0][kKphysPitch]; column kL holds K[q][L] (Nyquist)
+
 struct ColOptParams {
     cf *ws;
-    const float4 *kpair;    // [kF0][kKP]: (K[q][k], K[-q][L-k]); slot 0: (K[q][0], K[q][L]); slot kSlots: (K[q][L/2], K[-q][L/2])
+    const cf *kphys;
     const cf *tw;           // exp(-2 pi i j / 1024)
-    const cf *twr;          // exp(-2 pi i k / 2048), k <= 512
     int64_t ntiles_total;
     int64_t nwork;          // ntiles_total * (kL / 8)
 };
@@ -231,11 +258,11 @@ struct ColOptParams {
 constexpr int kColPitch = 32 * 8 + 8;   // padded k1-row stride of the exchange buffer (complex elements)
 constexpr int kColSmem = (1024 + 32 * kColPitch) * 8;
 
-__global__ void __launch_bounds__(256, 2) col_pair_fmi(const __grid_constant__ ColOptParams p)
+__global__ void __launch_bounds__(256, 2) col_fmi(const __grid_constant__ ColOptParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cf *s_tw = reinterpret_cast<cf *>(smem_raw);        // 1024
-    cf *S = s_tw + 1024;                                // 32 * kColPitch  (>= 1024 * 8 linear)
+    cf *S = s_tw + 1024;                                // 32 * kColPitch
     const int tid = threadIdx.x;
     const int c = tid & 7, i = tid >> 3;
     load_tw_table(s_tw, p.tw, tid, blockDim.x);
@@ -254,51 +281,39 @@ __global__ void __launch_bounds__(256, 2) col_pair_fmi(const __grid_constant__ C
         __syncthreads();
 #pragma unroll
         for (int ii = 0; ii < 32; ii++) v[ii] = S[i * kColPitch + ii * 8 + c];
-        dft32<float>(v, false);                            // v[k2] = Zhat[q = i + 32 k2][column]
-        __syncthreads();
+        dft32<float>(v, false);                            // v[k2] = Xhat[q = i + 32 k2][column]
+        // ---- multiply by the kernel spectrum (rows q = i + 32 k2 stay in this thread for the inverse) ----
+        const cf *kp = p.kphys + cb * 8 + c;
+        if (cb == 0) {
+            // physical column 0 = DC + i Nyquist of every row: separate the two real sequences through the q <-> -q mirror
+            __syncthreads();
+            if (c == 0) {
 #pragma unroll
-        for (int k2 = 0; k2 < 32; k2++) S[(i + 32 * k2) * 8 + c] = v[k2];
-        __syncthreads();
-        // ---- pair algebra: X = E + w^k O ; Y = X K ; re-pack ----
-        const int slot = cb * 4 + (c >> 1);
-        const int odd = c & 1;
-        const int role = slot ? odd : 2 + odd;               // 0 primary, 1 secondary, 2 DC/Nyquist, 3 middle (self-paired)
-        const int bcol = (role <= 1) ? (c ^ 1) : c;
-        const cf wk = p.twr[role == 3 ? kSlots : slot];
-        const int kslot = role == 3 ? kSlots : slot;
-#pragma unroll
-        for (int j = 0; j < 32; j++) {
-            const int q = i + 32 * j, qm = (kF0 - q) & (kF0 - 1);
-            const cf a = S[q * 8 + c], b = S[qm * 8 + bcol];
-            const float4 kk = __ldg(p.kpair + (int64_t)(role == 1 ? qm : q) * kKP + kslot);
-            const cf K0 = cf{kk.x, kk.y}, K1 = cf{kk.z, kk.w};
-            const cf ap = (role == 1) ? b : a, bp = (role == 1) ? a : b;
-            const cf E = cf{0.5f * (ap.re + bp.re), 0.5f * (ap.im - bp.im)};          // (ap + conj bp) / 2
-            const cf O = cf{0.5f * (ap.im + bp.im), -0.5f * (ap.re - bp.re)};         // -i (ap - conj bp) / 2
-            cf out;
-            if (role == 2) {
-                const cf Yd = cmul(cadd(E, O), K0), Yn = cmul(csub(E, O), K1);
-                const cf sm = cadd(Yd, Yn), df = csub(Yd, Yn);
-                out = cf{sm.re - df.im, sm.im + df.re};                               // sm + i df
-            } else {
-                const cf t = cmul(wk, O);
-                const cf X1 = cadd(E, t), X2 = cconj(csub(E, t));
-                const cf Y1 = cmul(X1, K0), Y2 = cmul(X2, K1);
-                if (role == 1) {
-                    const cf sm = cadd(Y2, cconj(Y1)), df = csub(Y2, cconj(Y1));
-                    const cf u = cmul(wk, df);                                        // out = sm - i w df
-                    out = cf{sm.re + u.im, sm.im - u.re};
-                } else {
-                    const cf sm = cadd(Y1, cconj(Y2)), df = csub(Y1, cconj(Y2));
-                    const cf u = cmulc(df, wk);                                       // out = sm + i conj(w) df
-                    out = cf{sm.re - u.im, sm.im + u.re};
-                }
+                for (int k2 = 0; k2 < 32; k2++) S[i + 32 * k2] = v[k2];
             }
-            v[j] = out;
+            __syncthreads();
+            if (c == 0) {
+#pragma unroll
+                for (int k2 = 0; k2 < 32; k2++) {
+                    const int q = i + 32 * k2, qm = (kF0 - q) & (kF0 - 1);
+                    const cf a = v[k2], b = S[qm];
+                    const cf A = cf{0.5f * (a.re + b.re), 0.5f * (a.im - b.im)};      // spectrum of the DC column
+                    const cf B = cf{0.5f * (a.im + b.im), -0.5f * (a.re - b.re)};     // spectrum of the Nyquist column
+                    const cf Yd = cmul(A, ld_cf(kp + (int64_t)q * kKphysPitch));
+                    const cf Yn = cmul(B, ld_cf(p.kphys + (int64_t)q * kKphysPitch + kL));
+                    v[k2] = cf{Yd.re - Yn.im, Yd.im + Yn.re};                         // Yd + i Yn
+                }
+            } else {
+#pragma unroll
+                for (int k2 = 0; k2 < 32; k2++) v[k2] = cmul(v[k2], ld_cf(kp + (int64_t)(i + 32 * k2) * kKphysPitch));
+            }
+        } else {
+#pragma unroll
+            for (int k2 = 0; k2 < 32; k2++) v[k2] = cmul(v[k2], ld_cf(kp + (int64_t)(i + 32 * k2) * kKphysPitch));
         }
-        // ---- inverse: radix 32 over j, conj twiddle, exchange, radix 32 over i ----
+        // ---- inverse: radix 32 over the register index, conj twiddle, exchange, radix 32 over i ----
         dft32<float>(v, true);
-        __syncthreads();                                   // every thread has finished reading the linear buffer
+        __syncthreads();                                   // every thread has finished reading S
 #pragma unroll
         for (int n1 = 0; n1 < 32; n1++) S[n1 * kColPitch + i * 8 + c] = cmulc(v[n1], s_tw[n1 * 32 + i]);
         __syncthreads();
@@ -313,26 +328,25 @@ __global__ void __launch_bounds__(256, 2) col_pair_fmi(const __grid_constant__ C
 
 }  // namespace opt
 
-// kernel spectrum [kF0][Hp] (bins 0..L) -> paired layout.  Block-stride body (host-emulable).
-struct KpairParams {
+// kernel spectrum [F0][Hp] (bins 0..L) -> physical column order of the paired layout:
+// column 0 <- bin 0, column 1 <- bin L/2, columns (2s, 2s+1) <- bins (s, L-s), column L <- bin L (Nyquist).
+struct KphysParams {
     const cx<float> *kspec;
-    float *kpair;     // float4 [F0][KP]
-    int F0, L, Hp, KP;
+    cx<float> *kphys;
+    int F0, L, Hp, pitch;
 };
-struct KpairBody {
-    static HD void run(const BlockCtx &c, const KpairParams &p)
+struct KphysBody {
+    static HD void run(const BlockCtx &c, const KphysParams &p)
     {
-        const int S = p.L / 2;
-        const int64_t total = (int64_t)p.F0 * (S + 1);
+        const int64_t total = (int64_t)p.F0 * (p.L + 1);
         for (int64_t e = c.bid * c.nt + c.tid; e < total; e += c.nb * c.nt) {
-            const int q = (int)(e / (S + 1)), slot = (int)(e % (S + 1));
-            const int qm = (p.F0 - q) % p.F0;
-            cx<float> a, b;
-            if (slot == 0) { a = p.kspec[(int64_t)q * p.Hp]; b = p.kspec[(int64_t)q * p.Hp + p.L]; }
-            else if (slot == S) { a = p.kspec[(int64_t)q * p.Hp + S]; b = p.kspec[(int64_t)qm * p.Hp + S]; }
-            else { a = p.kspec[(int64_t)q * p.Hp + slot]; b = p.kspec[(int64_t)qm * p.Hp + (p.L - slot)]; }
-            float *d = p.kpair + ((int64_t)q * p.KP + slot) * 4;
-            d[0] = a.re; d[1] = a.im; d[2] = b.re; d[3] = b.im;
+            const int q = (int)(e / (p.L + 1)), pc = (int)(e % (p.L + 1));
+            int bin;
+            if (pc == p.L) bin = p.L;
+            else if (pc == 0) bin = 0;
+            else if (pc == 1) bin = p.L / 2;
+            else bin = (pc & 1) ? p.L - (pc >> 1) : (pc >> 1);
+            p.kphys[(int64_t)q * p.pitch + pc] = p.kspec[(int64_t)q * p.Hp + bin];
         }
     }
 };
