@@ -235,6 +235,8 @@ def run_gpu(args, w, rank, world, local_rank):
         dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
     ms_max = float(t_dev.item())
 
+    shapes = other_shapes(pkg, lib, proc, dev, stream) if (rank == 0 and not args.no_shapes) else None
+
     # ---- e2e: host buffers through the C-ABI host call (H2D + kernels + D2H inside the timed region) ----
     proc.set_stream(0)   # the host call synchronises on the processor's own stream
     def step_host():
@@ -282,12 +284,66 @@ def run_gpu(args, w, rank, world, local_rank):
             "parity_spot_check": spot,
             "workspace_bytes": proc.workspace_bytes,
         }
+        if shapes is not None:
+            line["other_shapes"] = shapes
         if cpu_v is not None:
             line["cpu_baseline"] = {"value": cpu_v, "unit": "Gsamples/s", "cores": os.cpu_count() or 1, "kind": "port", "sample": cpu_s, "ms": cpu_t * 1e3}
         print(json.dumps(line), flush=True)
     proc.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def other_shapes(pkg, lib, proc, dev, stream):
+    """BASELINE configs[0..3] (parity-test shapes; latency-bound, microseconds): device-resident, warm processor,
+    CUDA events around 50 back-to-back calls.  Secondary per-shape numbers, not the headline."""
+    import torch
+    B = pkg.BorderType
+    cfgs = [
+        ("c1 1D f32 x=5000 k=31 Same Zeros", "fft", np.float32, (5000,), (31,), 1, pkg.ConvMode.Same, pkg.PaddingMode.Zeros),
+        ("c2 2D f32 x=(200,5000) k=(11,31) dil2 Same [Reflect,Circular]", "fft", np.float32, (200, 5000), (11, 31), 2, pkg.ConvMode.Same,
+         pkg.PaddingMode.Custom([B.Reflect, B.Circular])),
+        ("c3 3D f32 x=(10,100,200) k=(5,11,31) Same Zeros", "fft", np.float32, (10, 100, 200), (5, 11, 31), 1, pkg.ConvMode.Same, pkg.PaddingMode.Zeros),
+        ("c3 3D Complex<f32> x=(10,100,200) k=(5,11,31) Same Zeros", "fft", np.complex64, (10, 100, 200), (5, 11, 31), 1, pkg.ConvMode.Same, pkg.PaddingMode.Zeros),
+        ("c4 3D direct conv i32 x=(64,256,256) k=(3,5,5) pad(1,2,2) stride 2 Replicate", "direct", np.int32, (64, 256, 256), (3, 5, 5), 1,
+         pkg.ConvMode.Custom([1, 2, 2], [2, 2, 2]), pkg.PaddingMode.Replicate),
+    ]
+    out = []
+    for ci, (name, path, dt, xs, ks, dil, mode, pm) in enumerate(cfgs):
+        rng = np.random.default_rng(1000 + ci)
+        if dt == np.int32:
+            xh = rng.integers(-128, 128, size=xs, dtype=np.int32)
+            kh = np.random.default_rng(2000 + ci).integers(-128, 128, size=ks, dtype=np.int32)
+        elif dt == np.complex64:
+            xh = (rng.random(xs, dtype=np.float32) + 1j * rng.random(xs, dtype=np.float32)).astype(np.complex64)
+            kr = np.random.default_rng(2000 + ci)
+            kh = (kr.random(ks, dtype=np.float32) + 1j * kr.random(ks, dtype=np.float32)).astype(np.complex64)
+        else:
+            xh = rng.random(xs, dtype=np.float32)
+            kh = np.random.default_rng(2000 + ci).random(ks, dtype=np.float32)
+        xd = torch.from_numpy(xh.view(np.float32) if dt == np.complex64 else xh).to(dev)
+        kw = pkg.with_dilation(kh, dil)
+        entry = "ndconv_conv_fft" if path == "fft" else "ndconv_conv_direct"
+        strides = [int(np.prod(xs[i + 1:])) for i in range(len(xs))]
+        oshape = pkg.conv_device(entry, proc, xd.data_ptr(), xs, strides, dt, kw, mode, pm, None)
+        n_out = int(np.prod(oshape))
+        yd = torch.empty(n_out * (2 if dt == np.complex64 else 1), dtype=torch.int32 if dt == np.int32 else torch.float32, device=dev)
+        call = lambda: pkg.conv_device(entry, proc, xd.data_ptr(), xs, strides, dt, kw, mode, pm, yd.data_ptr())
+        for _ in range(5):
+            call()
+        torch.cuda.synchronize(dev)
+        reps = 50
+        l0 = proc.launch_count
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(reps):
+            call()
+        e1.record(stream)
+        torch.cuda.synchronize(dev)
+        us = e0.elapsed_time(e1) * 1e3 / reps
+        out.append({"shape": name, "us_per_call": us, "Gsamples_per_s": n_out / us / 1e3, "launches_per_call": (proc.launch_count - l0) / reps,
+                    "note": "device-resident, warm processor, includes host-side planning of every call"})
+    return out
 
 
 def spot_check(x_host, k, y_dev, pf0, pf1, padding, dil, rows, n1, n=48):
@@ -358,6 +414,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-shapes", action="store_true", help="skip the secondary per-shape numbers (configs c1-c4)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -161,9 +161,16 @@ struct ndconv_processor {
     uint64_t tick = 0;
     Profiler prof;
     LaunchCtx lc() { return LaunchCtx{stream, &launches, &prof}; }
+    // host-path slab pipeline (H2D | kernels | D2H overlapped)
+    DevBuf pipe_in[2], pipe_out[2], pipe_row;
+    stream_t h2d_stream = nullptr, d2h_stream = nullptr;
+#ifdef NDCONV_CUDA
+    cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
+#endif
+    int64_t pipelined_slabs = 0;
     size_t held() const
     {
-        size_t s = ws.cap + in_stage.cap + out_stage.cap + meta.cap + kb_stage.cap + kmeta.cap;
+        size_t s = ws.cap + in_stage.cap + out_stage.cap + meta.cap + kb_stage.cap + kmeta.cap + pipe_in[0].cap + pipe_in[1].cap + pipe_out[0].cap + pipe_out[1].cap;
         for (auto &k : kspecs) s += k->buf.cap + k->pair.cap;
         return s;
     }
@@ -682,12 +689,125 @@ static int conv_fft_t(ndconv_processor *p, const ndconv_problem *pr, Geom &g, st
     return NDCONV_OK;
 }
 
+static int conv_fft_impl(ndconv_processor *p, const ndconv_problem *pr, void *out);
+
+#ifdef NDCONV_CUDA
+// Host-resident problems that are large against PCIe: cut the OUTPUT rows of axis 0 into overlap-save slabs and run
+// H2D(slab s+1) | kernels(slab s) | D2H(slab s-1) on three streams.  Axis-0 padding of a slab is materialised while
+// staging (each padded row is copied from the source row its border map names; constant / never-written rows are
+// filled), which is exactly "pad axis 0 first" of the reference's sequential definition (src/padding/mod.rs:119-153),
+// so the slab runs as a plain device problem with no axis-0 border.
+static const size_t kPipelineMinBytes = 96u << 20;
+static const size_t kPipelineSlabBytes = 160u << 20;
+
+static bool pipeline_eligible(const ndconv_problem *pr, const Geom &g)
+{
+    static const bool disabled = getenv("NDCONV_DISABLE_PIPELINE") != nullptr;
+    if (disabled || pr->memory != NDCONV_MEM_HOST || !g.data_contiguous) return false;
+    const size_t bytes = ((size_t)g.data_total + (size_t)g.out_total) * g.es;
+    return bytes >= kPipelineMinBytes && g.O[0] >= 4;
+}
+
+static int conv_fft_host_pipelined(ndconv_processor *p, const ndconv_problem *pr, const Geom &g, const std::vector<int32_t> &map0, void *out)
+{
+    const int N = g.ndim;
+    int st;
+    if (!p->h2d_stream) {
+        CU_CHECK(cudaStreamCreateWithFlags(&p->h2d_stream, cudaStreamNonBlocking));
+        CU_CHECK(cudaStreamCreateWithFlags(&p->d2h_stream, cudaStreamNonBlocking));
+        for (int b = 0; b < 2; b++) {
+            CU_CHECK(cudaEventCreateWithFlags(&p->ev_h2d[b], cudaEventDisableTiming));
+            CU_CHECK(cudaEventCreateWithFlags(&p->ev_comp[b], cudaEventDisableTiming));
+            CU_CHECK(cudaEventCreateWithFlags(&p->ev_d2h[b], cudaEventDisableTiming));
+        }
+    }
+    int64_t in_row_elems = 1, out_row_elems = 1;
+    for (int a = 1; a < N; a++) { in_row_elems *= g.n[a]; out_row_elems *= g.O[a]; }
+    const size_t in_row_bytes = (size_t)in_row_elems * g.es, out_row_bytes = (size_t)out_row_elems * g.es;
+    // slab height in output rows: a multiple of the axis-0 tile payload so no tile is cut
+    FftPlan fullpl; st = make_plan(g, &fullpl); if (st) return st;
+    const int64_t V0 = std::max<int64_t>(1, fullpl.tl[0].V / g.s[0]);
+    int64_t rows = (int64_t)(kPipelineSlabBytes / std::max<size_t>(1, std::max(in_row_bytes * g.s[0], out_row_bytes)));
+    rows = std::max<int64_t>(V0, rows / V0 * V0);
+    if (rows >= g.O[0]) rows = std::max<int64_t>(1, (g.O[0] + 1) / 2);
+    const int64_t nslab = (g.O[0] + rows - 1) / rows;
+    const int64_t max_in_rows = (rows - 1) * g.s[0] + g.Kd[0];
+    for (int b = 0; b < 2; b++) {
+        st = p->pipe_in[b].reserve((size_t)max_in_rows * in_row_bytes); if (st) return st;
+        st = p->pipe_out[b].reserve((size_t)rows * out_row_bytes); if (st) return st;
+    }
+    // one host row holding the front / back constants of axis 0 (for constant border rows)
+    const bool has_const = g.bf[0] == NDCONV_BORDER_CONST || g.bb[0] == NDCONV_BORDER_CONST;
+    std::vector<unsigned char> crow_f, crow_b;
+    if (has_const) {
+        crow_f.resize(in_row_bytes); crow_b.resize(in_row_bytes);
+        for (int64_t e = 0; e < in_row_elems; e++) { memcpy(&crow_f[e * g.es], pr->border[0][0].value, g.es); memcpy(&crow_b[e * g.es], pr->border[0][1].value, g.es); }
+        st = p->pipe_row.reserve(2 * in_row_bytes); if (st) return st;
+        st = be_h2d(p->pipe_row.p, crow_f.data(), in_row_bytes, p->h2d_stream); if (st) return st;
+        st = be_h2d((char *)p->pipe_row.p + in_row_bytes, crow_b.data(), in_row_bytes, p->h2d_stream); if (st) return st;
+    }
+    const stream_t comp = p->stream;
+    const char *hx = (const char *)pr->data;
+    char *hout = (char *)out;
+    for (int64_t sidx = 0; sidx < nslab; sidx++) {
+        const int b = (int)(sidx & 1);
+        const int64_t ob = sidx * rows, oe = std::min<int64_t>(g.O[0], ob + rows);
+        const int64_t pb = ob * g.s[0], pe = (oe - 1) * g.s[0] + g.Kd[0];       // padded rows read by this slab
+        // ---- H2D: materialise padded rows [pb, pe) of axis 0 ----
+        if (sidx >= 2) CU_CHECK(cudaStreamWaitEvent(p->h2d_stream, p->ev_comp[b], 0));   // kernels of slab s-2 have consumed pipe_in[b]
+        char *din = (char *)p->pipe_in[b].p;
+        for (int64_t i = pb; i < pe;) {
+            const int32_t m = map0[(size_t)i];
+            char *drow = din + (size_t)(i - pb) * in_row_bytes;
+            if (m >= 0) {
+                int64_t run = 1;
+                while (i + run < pe && map0[(size_t)(i + run)] == m + (int32_t)run) run++;
+                st = be_h2d(drow, hx + (size_t)m * in_row_bytes, (size_t)run * in_row_bytes, p->h2d_stream); if (st) return st;
+                i += run;
+            } else if (m == NDC_MAP_INIT || (m == NDC_MAP_CONST_FRONT && g.bf[0] != NDCONV_BORDER_CONST) || (m == NDC_MAP_CONST_BACK && g.bb[0] != NDCONV_BORDER_CONST)) {
+                CU_CHECK(cudaMemsetAsync(drow, 0, in_row_bytes, p->h2d_stream));
+                i++;
+            } else {
+                const char *srow = (const char *)p->pipe_row.p + (m == NDC_MAP_CONST_BACK ? in_row_bytes : 0);
+                CU_CHECK(cudaMemcpyAsync(drow, srow, in_row_bytes, cudaMemcpyDeviceToDevice, p->h2d_stream));
+                i++;
+            }
+        }
+        CU_CHECK(cudaEventRecord(p->ev_h2d[b], p->h2d_stream));
+        // ---- kernels ----
+        CU_CHECK(cudaStreamWaitEvent(comp, p->ev_h2d[b], 0));
+        if (sidx >= 2) CU_CHECK(cudaStreamWaitEvent(comp, p->ev_d2h[b], 0));             // pipe_out[b] has been drained
+        ndconv_problem sub = *pr;
+        sub.memory = NDCONV_MEM_DEVICE;
+        sub.data = din;
+        sub.data_shape[0] = pe - pb;
+        { int64_t stn = 1; for (int a = N - 1; a >= 0; a--) { sub.data_strides[a] = stn; stn *= (a == 0 ? pe - pb : g.n[a]); } }
+        sub.pad[0][0] = sub.pad[0][1] = 0;
+        sub.border[0][0].type = sub.border[0][1].type = NDCONV_BORDER_ZEROS;
+        st = conv_fft_impl(p, &sub, p->pipe_out[b].p); if (st) return st;
+        CU_CHECK(cudaEventRecord(p->ev_comp[b], comp));
+        // ---- D2H ----
+        CU_CHECK(cudaStreamWaitEvent(p->d2h_stream, p->ev_comp[b], 0));
+        st = be_d2h(hout + (size_t)ob * out_row_bytes, p->pipe_out[b].p, (size_t)(oe - ob) * out_row_bytes, p->d2h_stream); if (st) return st;
+        CU_CHECK(cudaEventRecord(p->ev_d2h[b], p->d2h_stream));
+        p->pipelined_slabs++;
+    }
+    st = be_sync(p->h2d_stream); if (st) return st;
+    st = be_sync(comp); if (st) return st;
+    st = be_sync(p->d2h_stream); if (st) return st;
+    return NDCONV_OK;
+}
+#endif
+
 static int conv_fft_impl(ndconv_processor *p, const ndconv_problem *pr, void *out)
 {
     Geom g; std::vector<int32_t> maps[NDC_MAX_DIM];
     int st = check_problem(pr, NDCONV_PATH_FFT, &g, maps); if (st) return st;
     if (!out) { set_error("null output pointer"); return NDCONV_ERR_BAD_ARG; }
     st = set_device(p); if (st) return st;
+#ifdef NDCONV_CUDA
+    if (pipeline_eligible(pr, g)) return conv_fft_host_pipelined(p, pr, g, maps[0], out);
+#endif
     if (g.dtype == NDCONV_F32 || g.dtype == NDCONV_C32) return conv_fft_t<float>(p, pr, g, maps, out);
     return conv_fft_t<double>(p, pr, g, maps, out);
 }
@@ -788,6 +908,13 @@ int ndconv_processor_destroy(ndconv_processor *p)
     set_device(p);
     be_sync(p->stream);
     p->ws.release(); p->in_stage.release(); p->out_stage.release(); p->meta.release(); p->kb_stage.release(); p->kmeta.release();
+    for (int b = 0; b < 2; b++) { p->pipe_in[b].release(); p->pipe_out[b].release(); }
+    p->pipe_row.release();
+#ifdef NDCONV_CUDA
+    if (p->h2d_stream) cudaStreamDestroy(p->h2d_stream);
+    if (p->d2h_stream) cudaStreamDestroy(p->d2h_stream);
+    for (int b = 0; b < 2; b++) { if (p->ev_h2d[b]) cudaEventDestroy(p->ev_h2d[b]); if (p->ev_comp[b]) cudaEventDestroy(p->ev_comp[b]); if (p->ev_d2h[b]) cudaEventDestroy(p->ev_d2h[b]); }
+#endif
     for (auto &kv : p->tw_c) be_free(kv.second);
     for (auto &kv : p->tw_r) be_free(kv.second);
     for (auto &k : p->kspecs) { k->buf.release(); k->pair.release(); }
