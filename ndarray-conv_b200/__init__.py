@@ -434,6 +434,27 @@ def conv_device(entry, processor: Processor, x_ptr, x_shape, x_strides_elems, dt
     return shp
 
 
+class PreparedConv:
+    """A lowered problem kept alive for repeated device-resident calls (only the data / output pointers change):
+    the per-call host cost is one ctypes call; the processor's plan cache makes the C side a key lookup + launches."""
+
+    def __init__(self, entry, processor: Processor, x_shape, x_strides_elems, dtype, kernel, conv_mode, padding_mode, explicit=None):
+        self.lib = processor.lib
+        self.processor = processor
+        self.fn = getattr(self.lib.c, entry)
+        kwd = _into_kwd(kernel)
+        self.pr, self._keep = make_problem(x_shape, x_strides_elems, 0, dtype, kwd, conv_mode, padding_mode, MEM_DEVICE, self.lib, explicit=explicit)
+        self.pr.data = 1   # placeholder so shape validation does not trip on a null pointer
+        self.out_shape = out_shape(self.pr, PATH_DIRECT if entry == "ndconv_conv_direct" else PATH_FFT, self.lib)
+        self._ref = ctypes.byref(self.pr)
+
+    def __call__(self, x_ptr, out_ptr):
+        self.pr.data = x_ptr
+        st = self.fn(self.processor.handle, self._ref, ctypes.c_void_p(out_ptr))
+        if st:
+            self.lib.check(st)
+
+
 def slab_plan(x_shape, dtype, kernel, conv_mode, padding_mode, path, n_slabs, slab, lib=None):
     """ndconv_slab_plan: the output rows of axis 0 owned by `slab` and the padded rows it reads."""
     lib = lib or get_library()

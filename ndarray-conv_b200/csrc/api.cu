@@ -149,7 +149,12 @@ struct KSpecEntry {
     uint64_t last_use = 0;
 };
 
+struct PlanEntry;
+struct PlanEntryDeleter { void operator()(PlanEntry *e) const; };
+
 struct ndconv_processor {
+    std::vector<std::unique_ptr<PlanEntry, PlanEntryDeleter>> plans;   // per-geometry cache: validated geometry, device border maps / taps, FFT plan
+    int64_t plan_hits = 0, plan_misses = 0;
     int device = 0;
     int num_sms = 148;
     stream_t own_stream = nullptr, stream = nullptr;
@@ -309,57 +314,6 @@ template <class T> static int run_direct_t(ndconv_processor *p, const DirectPara
     return launch<DirectBody<T>, DirectParams>(p->lc(), "direct_conv", alg_bytes, grid, block, 0, dp);
 }
 
-static int conv_direct_impl(ndconv_processor *p, const ndconv_problem *pr, void *out)
-{
-    Geom g; std::vector<int32_t> maps[NDC_MAX_DIM];
-    int st = check_problem(pr, NDCONV_PATH_DIRECT, &g, maps); if (st) return st;
-    if (!out) { set_error("null output pointer"); return NDCONV_ERR_BAD_ARG; }
-    st = set_device(p); if (st) return st;
-    // taps are expressed on the device-side strides of x, so stage first
-    const void *dev_x = nullptr;
-    st = stage_input(p, pr, g, &dev_x); if (st) return st;
-    std::vector<unsigned char> kpacked((size_t)g.kernel_total * g.es);
-    pack_strided(pr->kernel, g.ndim, g.k, g.kstr, g.es, kpacked.data());
-    { int64_t s = 1; for (int i = g.ndim - 1; i >= 0; i--) { g.kstr[i] = s; s *= g.k[i]; } }
-    Taps taps; build_taps(g, kpacked.data(), taps);
-    MetaLayout ml;
-    st = upload_meta(p, p->meta, g, maps, &taps, &ml); if (st) return st;
-
-    DirectParams dp; memset(&dp, 0, sizeof(dp));
-    dp.ndim = g.ndim; dp.ntap = taps.ntap; dp.x = dev_x; dp.total = g.out_total;
-    const unsigned char *mb = (const unsigned char *)p->meta.p;
-    for (int a = 0; a < g.ndim; a++) {
-        dp.xstr[a] = g.xstr[a]; dp.n[a] = g.n[a]; dp.P[a] = g.P[a]; dp.pf[a] = g.pf[a]; dp.Kd[a] = g.Kd[a]; dp.s[a] = g.s[a]; dp.O[a] = g.O[a];
-        dp.map[a] = (const int32_t *)(mb + ml.map_off[a]);
-    }
-    dp.tap_off = (const int32_t *)(mb + ml.tap_off_off);
-    dp.tap_lin = (const int64_t *)(mb + ml.tap_lin_off);
-    dp.tap_w = mb + ml.tap_w_off;
-    fill_consts(pr, g.ndim, dp.cfront, dp.cback);
-    size_t obytes = (size_t)g.out_total * g.es;
-    if (pr->memory == NDCONV_MEM_HOST) { st = p->out_stage.reserve(obytes); if (st) return st; dp.out = p->out_stage.p; }
-    else dp.out = out;
-
-    const double alg_bytes = (double)g.es * ((double)g.data_total + (double)g.out_total + (double)taps.ntap);
-    switch (g.dtype) {
-    case NDCONV_I8: case NDCONV_U8: st = run_direct_t<uint8_t>(p, dp, alg_bytes); break;
-    case NDCONV_I16: case NDCONV_U16: st = run_direct_t<uint16_t>(p, dp, alg_bytes); break;
-    case NDCONV_I32: case NDCONV_U32: st = run_direct_t<uint32_t>(p, dp, alg_bytes); break;
-    case NDCONV_I64: case NDCONV_U64: st = run_direct_t<uint64_t>(p, dp, alg_bytes); break;
-    case NDCONV_F32: st = run_direct_t<float>(p, dp, alg_bytes); break;
-    case NDCONV_F64: st = run_direct_t<double>(p, dp, alg_bytes); break;
-    case NDCONV_C32: st = run_direct_t<cx<float>>(p, dp, alg_bytes); break;
-    case NDCONV_C64: st = run_direct_t<cx<double>>(p, dp, alg_bytes); break;
-    default: set_error("dtype"); st = NDCONV_ERR_BAD_ARG;
-    }
-    if (st) return st;
-    if (pr->memory == NDCONV_MEM_HOST) {
-        st = be_d2h(out, p->out_stage.p, obytes, p->stream); if (st) return st;
-        st = be_sync(p->stream); if (st) return st;
-    }
-    return NDCONV_OK;
-}
-
 // ======================================================================================================
 // FFT convolution
 // ======================================================================================================
@@ -418,6 +372,153 @@ static int make_plan(const Geom &g, FftPlan *pl)
     for (int a = 0; a < N - 1; a++) pl->rows_per_tile *= pl->tl[a].F;
     for (int a = 0; a < N; a++) pl->ntiles_total *= pl->tl[a].ntiles;
     pl->tile_elems = pl->rows_per_tile * pl->Hp;
+    return NDCONV_OK;
+}
+
+// ======================================================================================================
+// plan cache
+// ======================================================================================================
+struct PlanEntry {
+    std::vector<unsigned char> key;
+    uint64_t last_use = 0;
+    Geom g;                      // xstr already normalised to the device-side layout
+    bool host_contiguous = true; // host problems: the caller's array is standard layout (no packing needed)
+    DevBuf meta;
+    MetaLayout ml;
+    int ntap = 0;
+    FftPlan pl;
+};
+void PlanEntryDeleter::operator()(PlanEntry *e) const { if (e) { e->meta.release(); delete e; } }
+
+static int get_plan_entry(ndconv_processor *p, const ndconv_problem *pr, int path, PlanEntry **out)
+{
+    if (!pr) { set_error("null problem"); return NDCONV_ERR_BAD_ARG; }
+    const int N = (pr->ndim >= 1 && pr->ndim <= NDC_MAX_DIM) ? pr->ndim : 0;
+    std::vector<unsigned char> key;
+    key.reserve(512);
+    auto push = [&](const void *d, size_t n) { key.insert(key.end(), (const unsigned char *)d, (const unsigned char *)d + n); };
+    const size_t es = dtype_size(pr->dtype);
+    std::vector<unsigned char> kpacked;
+    bool keyable = N > 0 && es > 0 && pr->kernel != nullptr;
+    if (keyable) {
+        int32_t hdr[5] = {path, pr->dtype, pr->ndim, pr->memory, pr->reverse};
+        push(hdr, sizeof(hdr));
+        for (int a = 0; a < N; a++) {
+            int64_t v[9] = {pr->data_shape[a], pr->data_strides[a], pr->kernel_shape[a], pr->kernel_strides[a], pr->dilation[a],
+                            pr->pad[a][0], pr->pad[a][1], pr->stride[a], 0};
+            push(v, sizeof(v));
+            push(&pr->border[a][0].type, 4); push(pr->border[a][0].value, 16);
+            push(&pr->border[a][1].type, 4); push(pr->border[a][1].value, 16);
+            if (pr->kernel_shape[a] < 0) keyable = false;
+        }
+    }
+    if (keyable && path == NDCONV_PATH_DIRECT) {
+        // the tap table depends on the kernel values
+        int64_t kt = 1;
+        for (int a = 0; a < N; a++) kt *= pr->kernel_shape[a];
+        if (kt > 0 && kt < (1 << 22)) {
+            kpacked.resize((size_t)kt * es);
+            pack_strided(pr->kernel, N, pr->kernel_shape, pr->kernel_strides, (int)es, kpacked.data());
+            push(kpacked.data(), kpacked.size());
+        } else keyable = false;
+    }
+    p->tick++;
+    if (keyable) {
+        for (auto &e : p->plans) if (e->key == key) { e->last_use = p->tick; p->plan_hits++; *out = e.get(); return NDCONV_OK; }
+    }
+    p->plan_misses++;
+    std::unique_ptr<PlanEntry, PlanEntryDeleter> ent(new PlanEntry());
+    ent->key = key;
+    ent->last_use = p->tick;
+    std::vector<int32_t> maps[NDC_MAX_DIM];
+    int st = check_problem(pr, path, &ent->g, maps); if (st) return st;
+    Geom &g = ent->g;
+    ent->host_contiguous = g.data_contiguous;
+    if (pr->memory == NDCONV_MEM_HOST) { int64_t sacc = 1; for (int i = g.ndim - 1; i >= 0; i--) { g.xstr[i] = sacc; sacc *= g.n[i]; } }
+    st = set_device(p); if (st) return st;
+    if (path == NDCONV_PATH_DIRECT) {
+        if (kpacked.empty()) { kpacked.resize((size_t)g.kernel_total * g.es); pack_strided(pr->kernel, g.ndim, g.k, g.kstr, g.es, kpacked.data()); }
+        { int64_t sacc = 1; for (int i = g.ndim - 1; i >= 0; i--) { g.kstr[i] = sacc; sacc *= g.k[i]; } }
+        Taps taps; build_taps(g, kpacked.data(), taps);
+        ent->ntap = taps.ntap;
+        st = upload_meta(p, ent->meta, g, maps, &taps, &ent->ml); if (st) return st;
+    } else {
+        st = make_plan(g, &ent->pl); if (st) return st;
+        st = upload_meta(p, ent->meta, g, maps, nullptr, &ent->ml); if (st) return st;
+    }
+    st = be_sync(p->stream); if (st) return st;      // the staging vector of upload_meta dies here
+    if (p->plans.size() >= 32) {
+        size_t victim = 0;
+        for (size_t i = 1; i < p->plans.size(); i++) if (p->plans[i]->last_use < p->plans[victim]->last_use) victim = i;
+        be_sync(p->stream);
+        p->plans.erase(p->plans.begin() + victim);
+    }
+    *out = ent.get();
+    p->plans.push_back(std::move(ent));
+    return NDCONV_OK;
+}
+
+// stage the data array of a host problem on the device (packing strided views), or use a device array in place
+static int stage_input2(ndconv_processor *p, const ndconv_problem *pr, const PlanEntry &e, const void **dev_x)
+{
+    if (pr->memory == NDCONV_MEM_DEVICE) { *dev_x = pr->data; return NDCONV_OK; }
+    const Geom &g = e.g;
+    size_t bytes = (size_t)g.data_total * g.es;
+    int st = p->in_stage.reserve(bytes); if (st) return st;
+    if (e.host_contiguous) return (*dev_x = p->in_stage.p, be_h2d(p->in_stage.p, pr->data, bytes, p->stream));
+    std::vector<unsigned char> tmp(bytes);
+    pack_strided(pr->data, g.ndim, g.n, pr->data_strides, g.es, tmp.data());
+    st = be_h2d(p->in_stage.p, tmp.data(), bytes, p->stream); if (st) return st;
+    st = be_sync(p->stream); if (st) return st;
+    *dev_x = p->in_stage.p;
+    return NDCONV_OK;
+}
+
+// ======================================================================================================
+// direct convolution
+// ======================================================================================================
+static int conv_direct_impl(ndconv_processor *p, const ndconv_problem *pr, void *out)
+{
+    PlanEntry *e = nullptr;
+    int st = get_plan_entry(p, pr, NDCONV_PATH_DIRECT, &e); if (st) return st;
+    if (!out) { set_error("null output pointer"); return NDCONV_ERR_BAD_ARG; }
+    st = set_device(p); if (st) return st;
+    const Geom &g = e->g;
+    const void *dev_x = nullptr;
+    st = stage_input2(p, pr, *e, &dev_x); if (st) return st;
+
+    DirectParams dp; memset(&dp, 0, sizeof(dp));
+    dp.ndim = g.ndim; dp.ntap = e->ntap; dp.x = dev_x; dp.total = g.out_total;
+    const unsigned char *mb = (const unsigned char *)e->meta.p;
+    for (int a = 0; a < g.ndim; a++) {
+        dp.xstr[a] = g.xstr[a]; dp.n[a] = g.n[a]; dp.P[a] = g.P[a]; dp.pf[a] = g.pf[a]; dp.Kd[a] = g.Kd[a]; dp.s[a] = g.s[a]; dp.O[a] = g.O[a];
+        dp.map[a] = (const int32_t *)(mb + e->ml.map_off[a]);
+    }
+    dp.tap_off = (const int32_t *)(mb + e->ml.tap_off_off);
+    dp.tap_lin = (const int64_t *)(mb + e->ml.tap_lin_off);
+    dp.tap_w = mb + e->ml.tap_w_off;
+    fill_consts(pr, g.ndim, dp.cfront, dp.cback);
+    size_t obytes = (size_t)g.out_total * g.es;
+    if (pr->memory == NDCONV_MEM_HOST) { st = p->out_stage.reserve(obytes); if (st) return st; dp.out = p->out_stage.p; }
+    else dp.out = out;
+
+    const double alg_bytes = (double)g.es * ((double)g.data_total + (double)g.out_total + (double)e->ntap);
+    switch (g.dtype) {
+    case NDCONV_I8: case NDCONV_U8: st = run_direct_t<uint8_t>(p, dp, alg_bytes); break;
+    case NDCONV_I16: case NDCONV_U16: st = run_direct_t<uint16_t>(p, dp, alg_bytes); break;
+    case NDCONV_I32: case NDCONV_U32: st = run_direct_t<uint32_t>(p, dp, alg_bytes); break;
+    case NDCONV_I64: case NDCONV_U64: st = run_direct_t<uint64_t>(p, dp, alg_bytes); break;
+    case NDCONV_F32: st = run_direct_t<float>(p, dp, alg_bytes); break;
+    case NDCONV_F64: st = run_direct_t<double>(p, dp, alg_bytes); break;
+    case NDCONV_C32: st = run_direct_t<cx<float>>(p, dp, alg_bytes); break;
+    case NDCONV_C64: st = run_direct_t<cx<double>>(p, dp, alg_bytes); break;
+    default: set_error("dtype"); st = NDCONV_ERR_BAD_ARG;
+    }
+    if (st) return st;
+    if (pr->memory == NDCONV_MEM_HOST) {
+        st = be_d2h(out, p->out_stage.p, obytes, p->stream); if (st) return st;
+        st = be_sync(p->stream); if (st) return st;
+    }
     return NDCONV_OK;
 }
 
@@ -565,7 +666,7 @@ static int get_kernel_spectrum(ndconv_processor *p, const ndconv_problem *pr, co
 
 #ifdef NDCONV_CUDA
 // sm_100a fast path: 2-D real f32, tiles 1024 x 2048 (kernels_fft_opt.cuh)
-static int conv_fft_opt2d(ndconv_processor *p, const ndconv_problem *pr, const Geom &g, const FftPlan &pl, const MetaLayout &ml,
+static int conv_fft_opt2d(ndconv_processor *p, const ndconv_problem *pr, const Geom &g, const FftPlan &pl, const MetaLayout &ml, const DevBuf &metabuf,
                           const void *dev_x, void *dev_out, KSpecEntry *ent)
 {
     using namespace ndc::opt;
@@ -584,7 +685,7 @@ static int conv_fft_opt2d(ndconv_processor *p, const ndconv_problem *pr, const G
     RowOptParams rp; memset(&rp, 0, sizeof(rp));
     for (int a = 0; a < 2; a++) {
         rp.n[a] = g.n[a]; rp.xstr[a] = g.xstr[a]; rp.P[a] = g.P[a]; rp.pf[a] = g.pf[a];
-        rp.map[a] = (const int32_t *)((const unsigned char *)p->meta.p + ml.map_off[a]);
+        rp.map[a] = (const int32_t *)((const unsigned char *)metabuf.p + ml.map_off[a]);
         rp.V[a] = pl.tl[a].V; rp.ntiles[a] = pl.tl[a].ntiles; rp.Kd[a] = (int)g.Kd[a]; rp.s[a] = g.s[a]; rp.O[a] = g.O[a];
         rp.cfront[a] = pr->border[a][0].type == NDCONV_BORDER_CONST ? *(const float *)pr->border[a][0].value : 0.f;
         rp.cback[a] = pr->border[a][1].type == NDCONV_BORDER_CONST ? *(const float *)pr->border[a][1].value : 0.f;
@@ -621,15 +722,16 @@ static int conv_fft_opt2d(ndconv_processor *p, const ndconv_problem *pr, const G
 #endif
 
 template <class R>
-static int conv_fft_t(ndconv_processor *p, const ndconv_problem *pr, Geom &g, std::vector<int32_t> *maps, void *out)
+static int conv_fft_t(ndconv_processor *p, const ndconv_problem *pr, PlanEntry *pe, void *out)
 {
+    const Geom &g = pe->g;
     const int N = g.ndim;
-    FftPlan pl;
-    int st = make_plan(g, &pl); if (st) return st;
+    const FftPlan &pl = pe->pl;
+    int st;
     const void *dev_x = nullptr;
-    st = stage_input(p, pr, g, &dev_x); if (st) return st;
-    MetaLayout ml;
-    st = upload_meta(p, p->meta, g, maps, nullptr, &ml); if (st) return st;
+    st = stage_input2(p, pr, *pe, &dev_x); if (st) return st;
+    const MetaLayout &ml = pe->ml;
+    DevBuf &metabuf = pe->meta;
     const cx<R> *kspec = nullptr;
     KSpecEntry *kent = nullptr;
     st = get_kernel_spectrum<R>(p, pr, g, pl, &kspec, &kent); if (st) return st;
@@ -640,7 +742,7 @@ static int conv_fft_t(ndconv_processor *p, const ndconv_problem *pr, Geom &g, st
 #ifdef NDCONV_CUDA
     if (pl.opt2d) {
         if constexpr (sizeof(R) == 4) {
-            st = conv_fft_opt2d(p, pr, g, pl, ml, dev_x, dev_out, kent); if (st) return st;
+            st = conv_fft_opt2d(p, pr, g, pl, ml, metabuf, dev_x, dev_out, kent); if (st) return st;
             if (pr->memory == NDCONV_MEM_HOST) {
                 st = be_d2h(out, dev_out, obytes, p->stream); if (st) return st;
                 st = be_sync(p->stream); if (st) return st;
@@ -654,7 +756,7 @@ static int conv_fft_t(ndconv_processor *p, const ndconv_problem *pr, Geom &g, st
     rp.ndim = N; rp.is_cx = pl.is_cx ? 1 : 0;
     for (int a = 0; a < N; a++) {
         rp.n[a] = g.n[a]; rp.xstr[a] = g.xstr[a]; rp.P[a] = g.P[a];
-        rp.map[a] = (const int32_t *)((const unsigned char *)p->meta.p + ml.map_off[a]);
+        rp.map[a] = (const int32_t *)((const unsigned char *)metabuf.p + ml.map_off[a]);
         rp.F[a] = pl.tl[a].F; rp.V[a] = pl.tl[a].V; rp.ntiles[a] = pl.tl[a].ntiles; rp.Kd[a] = (int)g.Kd[a];
         rp.s[a] = g.s[a]; rp.O[a] = g.O[a];
     }
@@ -801,15 +903,20 @@ static int conv_fft_host_pipelined(ndconv_processor *p, const ndconv_problem *pr
 
 static int conv_fft_impl(ndconv_processor *p, const ndconv_problem *pr, void *out)
 {
-    Geom g; std::vector<int32_t> maps[NDC_MAX_DIM];
-    int st = check_problem(pr, NDCONV_PATH_FFT, &g, maps); if (st) return st;
+#ifdef NDCONV_CUDA
+    if (pr && pr->memory == NDCONV_MEM_HOST) {
+        Geom g; std::vector<int32_t> maps[NDC_MAX_DIM];
+        int st0 = check_problem(pr, NDCONV_PATH_FFT, &g, maps); if (st0) return st0;
+        if (!out) { set_error("null output pointer"); return NDCONV_ERR_BAD_ARG; }
+        if (pipeline_eligible(pr, g)) { st0 = set_device(p); if (st0) return st0; return conv_fft_host_pipelined(p, pr, g, maps[0], out); }
+    }
+#endif
+    PlanEntry *pe = nullptr;
+    int st = get_plan_entry(p, pr, NDCONV_PATH_FFT, &pe); if (st) return st;
     if (!out) { set_error("null output pointer"); return NDCONV_ERR_BAD_ARG; }
     st = set_device(p); if (st) return st;
-#ifdef NDCONV_CUDA
-    if (pipeline_eligible(pr, g)) return conv_fft_host_pipelined(p, pr, g, maps[0], out);
-#endif
-    if (g.dtype == NDCONV_F32 || g.dtype == NDCONV_C32) return conv_fft_t<float>(p, pr, g, maps, out);
-    return conv_fft_t<double>(p, pr, g, maps, out);
+    if (pe->g.dtype == NDCONV_F32 || pe->g.dtype == NDCONV_C32) return conv_fft_t<float>(p, pr, pe, out);
+    return conv_fft_t<double>(p, pr, pe, out);
 }
 
 // ======================================================================================================
