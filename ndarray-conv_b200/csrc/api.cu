@@ -17,6 +17,7 @@
 #include "kernels_direct.h"
 #include "kernels_fft.h"
 #include "kernels_fft_opt.cuh"
+#include "kernels_direct_tile.cuh"
 
 #ifdef NDCONV_CUDA
 #include <cuda_runtime.h>
@@ -168,6 +169,7 @@ struct ndconv_processor {
     LaunchCtx lc() { return LaunchCtx{stream, &launches, &prof}; }
     // host-path slab pipeline (H2D | kernels | D2H overlapped)
     DevBuf pipe_in[2], pipe_out[2], pipe_row;
+    DevBuf zero_map;             // one int32 0: identity border map of the dummy leading axes of the rank-3 tile kernel
     stream_t h2d_stream = nullptr, d2h_stream = nullptr;
 #ifdef NDCONV_CUDA
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
@@ -474,6 +476,138 @@ static int stage_input2(ndconv_processor *p, const ndconv_problem *pr, const Pla
     return NDCONV_OK;
 }
 
+#ifdef NDCONV_CUDA
+// ---- sm_100a tile-plus-halo direct convolution (kernels_direct_tile.cuh) -------------------------------------
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                        const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_tmapEncodeTiled get_tmap_encoder()
+{
+    static PFN_tmapEncodeTiled fn = [] {
+        void *f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) { cudaGetLastError(); f = nullptr; }
+        return (PFN_tmapEncodeTiled)f;
+    }();
+    return fn;
+}
+
+static bool value_is_zero(const ndconv_border &b, int es)
+{
+    if (b.type == NDCONV_BORDER_ZEROS) return true;
+    if (b.type != NDCONV_BORDER_CONST) return false;
+    for (int i = 0; i < es; i++) if (b.value[i]) return false;
+    return true;
+}
+
+template <class T>
+static int launch_direct_tile(ndconv_processor *p, const CUtensorMap &tm, const tile::TileParams &tp, int64_t grid, size_t smem, double alg_bytes)
+{
+    static bool attr_set = false;
+    if (!attr_set) { CU_CHECK(cudaFuncSetAttribute(tile::direct_tile_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr_set = true; }
+    const stream_t stm = p->stream;
+    return launch_raw(p->lc(), tp.use_tma ? "direct_conv_tile_tma" : "direct_conv_tile", alg_bytes,
+                      [&] { tile::direct_tile_kernel<T><<<(unsigned)grid, tile::kThreads, smem, stm>>>(tm, tp); });
+}
+
+// returns NDCONV_OK with *used = false when the problem is outside the tile kernel's envelope (caller falls back)
+static int try_direct_tile(ndconv_processor *p, const ndconv_problem *pr, const PlanEntry &e, const void *dev_x, void *dev_out, bool *used)
+{
+    *used = false;
+    static const bool disabled = getenv("NDCONV_DISABLE_TILE") != nullptr;
+    const Geom &g = e.g;
+    if (disabled || g.ndim > 3 || e.ntap == 0) return NDCONV_OK;
+    const int sh = 3 - g.ndim, es = g.es;
+    tile::TileParams tp; memset(&tp, 0, sizeof(tp));
+    int st;
+    if (!p->zero_map.p) {
+        st = p->zero_map.reserve(16); if (st) return st;
+        CU_CHECK(cudaMemsetAsync(p->zero_map.p, 0, 16, p->stream));
+    }
+    const unsigned char *mb = (const unsigned char *)e.meta.p;
+    for (int a3 = 0; a3 < 3; a3++) {
+        const int a = a3 - sh;
+        if (a < 0) {
+            tp.n[a3] = 1; tp.xstr[a3] = 0; tp.P[a3] = 1; tp.pf[a3] = 0; tp.Kd[a3] = 1; tp.s[a3] = 1; tp.O[a3] = 1;
+            tp.map[a3] = (const int32_t *)p->zero_map.p; tp.front_zero[a3] = tp.back_zero[a3] = 1;
+        } else {
+            tp.n[a3] = g.n[a]; tp.xstr[a3] = g.xstr[a]; tp.P[a3] = g.P[a]; tp.pf[a3] = g.pf[a]; tp.Kd[a3] = g.Kd[a]; tp.s[a3] = g.s[a]; tp.O[a3] = g.O[a];
+            tp.map[a3] = (const int32_t *)(mb + e.ml.map_off[a]);
+            memset(tp.cfront[a3], 0, 16); memset(tp.cback[a3], 0, 16);
+            if (pr->border[a][0].type == NDCONV_BORDER_CONST) memcpy(tp.cfront[a3], pr->border[a][0].value, 16);
+            if (pr->border[a][1].type == NDCONV_BORDER_CONST) memcpy(tp.cback[a3], pr->border[a][1].value, 16);
+            tp.front_zero[a3] = value_is_zero(pr->border[a][0], es); tp.back_zero[a3] = value_is_zero(pr->border[a][1], es);
+        }
+    }
+    if (tp.Kd[0] > (1 << 20) || tp.Kd[1] > (1 << 20) || tp.Kd[2] > (1 << 20)) return NDCONV_OK;
+    tp.ostr[2] = 1; tp.ostr[1] = tp.O[2]; tp.ostr[0] = tp.O[1] * tp.O[2];
+    // tile shape
+    auto np2 = [](int64_t v) { int r = 1; while (r < v && r < 256) r <<= 1; return r; };
+    int TO2 = np2(tp.O[2]);
+    while (TO2 > 32 && (tile::kThreads / TO2) < std::min<int64_t>(tp.O[1], 8)) TO2 >>= 1;
+    int TO1 = (int)std::min<int64_t>(tile::kThreads / TO2, np2(tp.O[1]));
+    int TO0 = (int)std::min<int64_t>(tile::kMaxTO0, tp.O[0]);
+    const int round = 16 / std::min(es, 16);
+    auto shape = [&](int T0, int T1, int T2) {
+        tp.TO[0] = T0; tp.TO[1] = T1; tp.TO[2] = T2;
+        for (int a = 0; a < 3; a++) tp.IT[a] = (int)((tp.TO[a] - 1) * tp.s[a] + tp.Kd[a]);
+        tp.IT2p = (tp.IT[2] + (round - 1) + round - 1) / round * round;   // + (round-1): room for the per-tile alignment shift
+        return (int64_t)tp.IT[0] * tp.IT[1] * tp.IT2p;
+    };
+    int64_t elems = shape(TO0, TO1, TO2);
+    const int64_t budget = 150 * 1024;
+    while (elems * es > budget && TO0 > 1) { TO0--; elems = shape(TO0, TO1, TO2); }
+    while (elems * es > budget && TO1 > 1) { TO1 >>= 1; elems = shape(TO0, TO1, TO2); }
+    while (elems * es > budget && TO2 > 1) { TO2 >>= 1; elems = shape(TO0, TO1, TO2); }
+    if (elems * es > budget) return NDCONV_OK;
+    const size_t tap_bytes = align_up((size_t)e.ntap * es, 16) + (size_t)e.ntap * 4;
+    const size_t tile_bytes = align_up((size_t)elems * es, 128);
+    if (tile_bytes + tap_bytes + 256 > 190 * 1024) return NDCONV_OK;
+    tp.tile_elems = (int)elems;
+    int64_t grid = 1;
+    for (int a = 0; a < 3; a++) { tp.ntile[a] = (int)((tp.O[a] + tp.TO[a] - 1) / tp.TO[a]); grid *= tp.ntile[a]; }
+    if (grid > 0x7fffffff) return NDCONV_OK;
+    tp.ntap = e.ntap; tp.axis_shift = sh;
+    tp.tap_off = (const int32_t *)(mb + e.ml.tap_off_off);
+    tp.tap_w = mb + e.ml.tap_w_off;
+    tp.x = dev_x; tp.out = dev_out;
+    // TMA eligibility: 4/8-byte elements, standard layout, 16-byte aligned rows
+    CUtensorMap tm; memset(&tm, 0, sizeof(tm));
+    bool tma = (es == 4 || es == 8) && tp.xstr[2] == 1 && (tp.n[1] == 1 || tp.xstr[1] == tp.n[2]) && (tp.n[0] == 1 || tp.xstr[0] == tp.n[1] * tp.n[2]) &&
+               ((tp.n[2] * es) % 16 == 0) && ((uintptr_t)dev_x % 16 == 0) && tp.IT[0] <= 256 && tp.IT[1] <= 256 && tp.IT2p <= 256 && get_tmap_encoder();
+    if (tma) {
+        cuuint64_t gdim[3] = {(cuuint64_t)tp.n[2], (cuuint64_t)tp.n[1], (cuuint64_t)tp.n[0]};
+        cuuint64_t gstr[2] = {(cuuint64_t)tp.n[2] * es, (cuuint64_t)tp.n[1] * tp.n[2] * es};
+        cuuint32_t box[3] = {(cuuint32_t)tp.IT2p, (cuuint32_t)tp.IT[1], (cuuint32_t)tp.IT[0]};
+        cuuint32_t estr[3] = {1, 1, 1};
+        CUresult r = get_tmap_encoder()(&tm, es == 4 ? CU_TENSOR_MAP_DATA_TYPE_UINT32 : CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, const_cast<void *>(dev_x), gdim, gstr, box, estr,
+                                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) tma = false;
+        if (getenv("NDCONV_DEBUG_TMA")) fprintf(stderr, "[ndconv] tmap encode r=%d es=%d gdim=(%llu,%llu,%llu) gstr=(%llu,%llu) box=(%u,%u,%u) x=%p\n", (int)r, es,
+            (unsigned long long)gdim[0], (unsigned long long)gdim[1], (unsigned long long)gdim[2], (unsigned long long)gstr[0], (unsigned long long)gstr[1], box[0], box[1], box[2], dev_x);
+    }
+    static const bool no_tma = getenv("NDCONV_DISABLE_TMA") != nullptr;
+    if (no_tma) tma = false;
+    tp.use_tma = tma ? 1 : 0;
+    const size_t smem = tile_bytes + tap_bytes + 128;
+    const double alg_bytes = (double)es * ((double)g.data_total + (double)g.out_total + (double)e.ntap);
+    switch (g.dtype) {
+    case NDCONV_I8: case NDCONV_U8: st = launch_direct_tile<uint8_t>(p, tm, tp, grid, smem, alg_bytes); break;
+    case NDCONV_I16: case NDCONV_U16: st = launch_direct_tile<uint16_t>(p, tm, tp, grid, smem, alg_bytes); break;
+    case NDCONV_I32: case NDCONV_U32: st = launch_direct_tile<uint32_t>(p, tm, tp, grid, smem, alg_bytes); break;
+    case NDCONV_I64: case NDCONV_U64: st = launch_direct_tile<uint64_t>(p, tm, tp, grid, smem, alg_bytes); break;
+    case NDCONV_F32: st = launch_direct_tile<float>(p, tm, tp, grid, smem, alg_bytes); break;
+    case NDCONV_F64: st = launch_direct_tile<double>(p, tm, tp, grid, smem, alg_bytes); break;
+    case NDCONV_C32: st = launch_direct_tile<cx<float>>(p, tm, tp, grid, smem, alg_bytes); break;
+    case NDCONV_C64: st = launch_direct_tile<cx<double>>(p, tm, tp, grid, smem, alg_bytes); break;
+    default: return NDCONV_OK;
+    }
+    if (st) return st;
+    *used = true;
+    return NDCONV_OK;
+}
+#endif
+
 // ======================================================================================================
 // direct convolution
 // ======================================================================================================
@@ -503,7 +637,12 @@ static int conv_direct_impl(ndconv_processor *p, const ndconv_problem *pr, void 
     else dp.out = out;
 
     const double alg_bytes = (double)g.es * ((double)g.data_total + (double)g.out_total + (double)e->ntap);
-    switch (g.dtype) {
+    bool tiled = false;
+#ifdef NDCONV_CUDA
+    st = try_direct_tile(p, pr, *e, dev_x, dp.out, &tiled); if (st) return st;
+#endif
+    if (tiled) st = NDCONV_OK;
+    else switch (g.dtype) {
     case NDCONV_I8: case NDCONV_U8: st = run_direct_t<uint8_t>(p, dp, alg_bytes); break;
     case NDCONV_I16: case NDCONV_U16: st = run_direct_t<uint16_t>(p, dp, alg_bytes); break;
     case NDCONV_I32: case NDCONV_U32: st = run_direct_t<uint32_t>(p, dp, alg_bytes); break;
@@ -1016,7 +1155,7 @@ int ndconv_processor_destroy(ndconv_processor *p)
     be_sync(p->stream);
     p->ws.release(); p->in_stage.release(); p->out_stage.release(); p->meta.release(); p->kb_stage.release(); p->kmeta.release();
     for (int b = 0; b < 2; b++) { p->pipe_in[b].release(); p->pipe_out[b].release(); }
-    p->pipe_row.release();
+    p->pipe_row.release(); p->zero_map.release();
 #ifdef NDCONV_CUDA
     if (p->h2d_stream) cudaStreamDestroy(p->h2d_stream);
     if (p->d2h_stream) cudaStreamDestroy(p->d2h_stream);
