@@ -339,7 +339,8 @@ static bool opt2d_eligible(const Geom &g)
 #ifdef NDCONV_CUDA
     static const bool disabled = getenv("NDCONV_DISABLE_OPT") != nullptr;
     if (disabled) return false;
-    return g.ndim == 2 && g.dtype == NDCONV_F32 && g.P[0] >= 600 && g.P[1] >= 1200 && g.Kd[0] <= 512 && g.Kd[1] <= 1024;
+    static const int min_p0 = getenv("NDCONV_OPT_MIN_P0") ? atoi(getenv("NDCONV_OPT_MIN_P0")) : 64;
+    return g.ndim == 2 && g.dtype == NDCONV_F32 && g.P[0] >= min_p0 && g.P[1] >= 1200 && g.Kd[0] <= 512 && g.Kd[1] <= 1024;
 #else
     (void)g;
     return false;
@@ -354,7 +355,16 @@ static int make_plan(const Geom &g, FftPlan *pl)
     pl->opt2d = opt2d_eligible(g);
     for (int a = 0; a < N; a++) {
         if (pl->opt2d) {
-            const int F = a == 0 ? 1024 : 2048;
+            int F = 2048;
+            if (a == 0) {
+                // column tile height: 1024 (radix 32x32) or 256 (radix 16x16), whichever transforms fewer rows in total
+                F = 1024;
+                if (g.Kd[0] <= 128) {
+                    const int64_t M0 = g.P[0] - g.Kd[0] + 1;
+                    const int64_t c1024 = ((M0 + (1024 - g.Kd[0])) / (1024 - g.Kd[0] + 1)) * 1024, c256 = ((M0 + (256 - g.Kd[0])) / (256 - g.Kd[0] + 1)) * 256;
+                    if (c256 < c1024) F = 256;
+                }
+            }
             pl->tl[a].F = F; pl->tl[a].V = F - (int)g.Kd[a] + 1;
             pl->tl[a].ntiles = (int)((g.P[a] - g.Kd[a] + 1 + pl->tl[a].V - 1) / pl->tl[a].V);
             if (!factor_radices(a == 0 ? F : F / 2, &pl->fl[a])) return NDCONV_ERR_INTERNAL;
@@ -363,6 +373,12 @@ static int make_plan(const Geom &g, FftPlan *pl)
         const bool last = (a == N - 1);
         const bool real_axis = last && !is_cx;
         int cap = last ? cap_last_axis(is_cx, is_dbl) : cap_col_axis(is_dbl);
+        if (N == 1) {
+            // a 1-D problem is one row: shorter overlap-save tiles = more CTAs in flight and fewer Stockham passes each
+            int c1 = 512;
+            while (c1 < 8 * g.Kd[a] && c1 < cap) c1 <<= 1;
+            cap = std::min(cap, c1);
+        }
         int st = plan_axis(g.P[a], g.Kd[a], cap, real_axis, &pl->tl[a]); if (st) return st;
         int L = real_axis ? pl->tl[a].F / 2 : pl->tl[a].F;
         if (!factor_radices(L, &pl->fl[a])) { set_error("internal: non-smooth FFT length"); return NDCONV_ERR_INTERNAL; }
@@ -810,15 +826,22 @@ static int conv_fft_opt2d(ndconv_processor *p, const ndconv_problem *pr, const G
 {
     using namespace ndc::opt;
     int st;
+    const int F0 = pl.tl[0].F;                      // 1024 or 256
     if (!ent->pair.p) {
-        st = ent->pair.reserve((size_t)kF0 * kKphysPitch * sizeof(cf)); if (st) return st;
-        KphysParams kp; kp.kspec = (const cx<float> *)ent->buf.p; kp.kphys = (cx<float> *)ent->pair.p; kp.F0 = kF0; kp.L = kL; kp.Hp = pl.Hp; kp.pitch = kKphysPitch;
-        st = launch<KphysBody, KphysParams>(p->lc(), "kspec_phys_repack", (double)kF0 * kKphysPitch * 16, p->num_sms * 4, 256, 0, kp); if (st) return st;
+        st = ent->pair.reserve((size_t)F0 * kKphysPitch * sizeof(cf)); if (st) return st;
+        KphysParams kp; kp.kspec = (const cx<float> *)ent->buf.p; kp.kphys = (cx<float> *)ent->pair.p; kp.F0 = F0; kp.L = kL; kp.Hp = pl.Hp; kp.pitch = kKphysPitch;
+        st = launch<KphysBody, KphysParams>(p->lc(), "kspec_phys_repack", (double)F0 * kKphysPitch * 16, p->num_sms * 4, 256, 0, kp); if (st) return st;
     }
-    const int64_t tile_elems = (int64_t)kF0 * kL;
-    st = p->ws.reserve((size_t)pl.ntiles_total * tile_elems * sizeof(cf)); if (st) return st;
+    const int64_t tile_elems = (int64_t)F0 * kL;
+    {
+        const char *bt = getenv("NDCONV_BATCH_TILES");
+        const int64_t ws_tiles = (bt && atoi(bt) > 0) ? std::min<int64_t>(atoi(bt), pl.tl[1].ntiles) : pl.ntiles_total;
+        st = p->ws.reserve((size_t)ws_tiles * tile_elems * sizeof(cf)); if (st) return st;
+    }
     const cx<float> *tw = nullptr, *twr = nullptr;
+    const cx<float> *tw_col = nullptr;
     st = get_tw_c<float>(p, kL, &tw); if (st) return st;
+    st = get_tw_c<float>(p, F0, &tw_col); if (st) return st;
     st = get_tw_r<float>(p, kF1, &twr); if (st) return st;
 
     RowOptParams rp; memset(&rp, 0, sizeof(rp));
@@ -829,32 +852,64 @@ static int conv_fft_opt2d(ndconv_processor *p, const ndconv_problem *pr, const G
         rp.cfront[a] = pr->border[a][0].type == NDCONV_BORDER_CONST ? *(const float *)pr->border[a][0].value : 0.f;
         rp.cback[a] = pr->border[a][1].type == NDCONV_BORDER_CONST ? *(const float *)pr->border[a][1].value : 0.f;
     }
-    rp.x = (const float *)dev_x; rp.out = (float *)dev_out; rp.ws = (cf *)p->ws.p; rp.tw = tw; rp.twr = twr;
+    rp.x = (const float *)dev_x; rp.out = (float *)dev_out; rp.ws = (cf *)p->ws.p; rp.tw = tw; rp.twr = twr; rp.F0 = F0;
 
     static bool attr_set = false;
-    if (!attr_set) { CU_CHECK(cudaFuncSetAttribute(col_fmi, cudaFuncAttributeMaxDynamicSharedMemorySize, kColSmem)); attr_set = true; }
+    if (!attr_set) {
+        CU_CHECK(cudaFuncSetAttribute(col_fmi<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, ColCfg<32>::smem));
+        CU_CHECK(cudaFuncSetAttribute(col_fmi<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ColCfg<16>::smem));
+        attr_set = true;
+    }
+    auto launch_col = [&](const ColOptParams &cpar, int grid_cap_mult) {
+        if (F0 == 1024) { const int grid = (int)std::min<int64_t>(cpar.nwork, (int64_t)p->num_sms * 2 * grid_cap_mult); col_fmi<32><<<grid, ColCfg<32>::threads, ColCfg<32>::smem, p->stream>>>(cpar); }
+        else { const int grid = (int)std::min<int64_t>(cpar.nwork, (int64_t)p->num_sms * 6 * grid_cap_mult); col_fmi<16><<<grid, ColCfg<16>::threads, ColCfg<16>::smem, p->stream>>>(cpar); }
+    };
 
     const double csz = 8.0;
     double S = (double)(g.P[1] / 2 + 1) * (double)g.P[0], So = (double)(g.P[1] / 2 + 1) * (double)g.O[0];
     const double in_bytes = 4.0 * (double)g.data_total, out_bytes = 4.0 * (double)g.out_total;
     const stream_t stm = p->stream;
 
-    rp.nwork = pl.ntiles_total * kF0;
-    {
-        const int grid = (int)std::min<int64_t>((rp.nwork + 3) / 4, (int64_t)p->num_sms * 4 * 8);
-        st = launch_raw(p->lc(), "row_fwd_pad_r2c", in_bytes + S * csz, [&] { row_fwd_packed<<<grid, 128, 0, stm>>>(rp); }); if (st) return st;
-    }
-    {
-        ColOptParams cp; cp.ws = (cf *)p->ws.p; cp.kphys = (const cf *)ent->pair.p; cp.tw = tw;
-        cp.ntiles_total = pl.ntiles_total; cp.nwork = pl.ntiles_total * (kL / 8);
-        const int grid = (int)std::min<int64_t>(cp.nwork, (int64_t)p->num_sms * 2);
-        st = launch_raw(p->lc(), "col_fwd_mul_inv", 2 * S * csz + (double)kF0 * kKphysPitch * 8,
-                        [&] { col_fmi<<<grid, 256, kColSmem, stm>>>(cp); }); if (st) return st;
-    }
-    rp.nwork = g.O[0] * pl.tl[1].ntiles;
-    {
-        const int grid = (int)std::min<int64_t>((rp.nwork + 3) / 4, (int64_t)p->num_sms * 4 * 8);
-        st = launch_raw(p->lc(), "row_inv_c2r_crop", So * csz + out_bytes, [&] { row_inv_packed<<<grid, 128, 0, stm>>>(rp); }); if (st) return st;
+    static const int batch_tiles = getenv("NDCONV_BATCH_TILES") ? atoi(getenv("NDCONV_BATCH_TILES")) : 0;
+    ColOptParams cp; cp.ws = (cf *)p->ws.p; cp.kphys = (const cf *)ent->pair.p; cp.tw = tw_col;
+    if (batch_tiles <= 0) {
+        rp.nwork = pl.ntiles_total * F0;
+        {
+            const int grid = (int)std::min<int64_t>((rp.nwork + 3) / 4, (int64_t)p->num_sms * 4 * 8);
+            st = launch_raw(p->lc(), "row_fwd_pad_r2c", in_bytes + S * csz, [&] { row_fwd_packed<<<grid, 128, 0, stm>>>(rp); }); if (st) return st;
+        }
+        {
+            cp.ntiles_total = pl.ntiles_total; cp.nwork = pl.ntiles_total * (kL / 8);
+            st = launch_raw(p->lc(), "col_fwd_mul_inv", 2 * S * csz + (double)F0 * kKphysPitch * 8, [&] { launch_col(cp, 1); }); if (st) return st;
+        }
+        rp.nwork = g.O[0] * pl.tl[1].ntiles;
+        {
+            const int grid = (int)std::min<int64_t>((rp.nwork + 3) / 4, (int64_t)p->num_sms * 4 * 8);
+            st = launch_raw(p->lc(), "row_inv_c2r_crop", So * csz + out_bytes, [&] { row_inv_packed<<<grid, 128, 0, stm>>>(rp); }); if (st) return st;
+        }
+    } else {
+        // L2-resident schedule: the three kernels run per batch of tiles that share one small workspace
+        const int nt0 = pl.tl[0].ntiles, nt1 = pl.tl[1].ntiles;
+        const double nb = (double)nt0 * ((nt1 + batch_tiles - 1) / batch_tiles);
+        rp.batch = 1;
+        for (int t0 = 0; t0 < nt0; t0++) {
+            const int64_t o_lo = ((int64_t)t0 * pl.tl[0].V + g.s[0] - 1) / g.s[0];
+            const int64_t o_hi = std::min<int64_t>(g.O[0], ((int64_t)(t0 + 1) * pl.tl[0].V + g.s[0] - 1) / g.s[0]);
+            for (int t1b = 0; t1b < nt1; t1b += batch_tiles) {
+                const int nb1 = std::min(batch_tiles, nt1 - t1b);
+                rp.b_t0 = t0; rp.b_t1 = t1b; rp.b_nt1 = nb1; rp.b_o0 = o_lo; rp.b_no0 = std::max<int64_t>(0, o_hi - o_lo);
+                rp.nwork = (int64_t)nb1 * F0;
+                int grid = (int)std::min<int64_t>((rp.nwork + 3) / 4, (int64_t)p->num_sms * 4 * 8);
+                st = launch_raw(p->lc(), "row_fwd_pad_r2c", (in_bytes + S * csz) / nb, [&] { row_fwd_packed<<<grid, 128, 0, stm>>>(rp); }); if (st) return st;
+                cp.ntiles_total = nb1; cp.nwork = (int64_t)nb1 * (kL / 8);
+                st = launch_raw(p->lc(), "col_fwd_mul_inv", (2 * S * csz) / nb, [&] { launch_col(cp, 1); }); if (st) return st;
+                rp.nwork = rp.b_no0 * nb1;
+                if (rp.nwork > 0) {
+                    grid = (int)std::min<int64_t>((rp.nwork + 3) / 4, (int64_t)p->num_sms * 4 * 8);
+                    st = launch_raw(p->lc(), "row_inv_c2r_crop", (So * csz + out_bytes) / nb, [&] { row_inv_packed<<<grid, 128, 0, stm>>>(rp); }); if (st) return st;
+                }
+            }
+        }
     }
     return NDCONV_OK;
 }

@@ -41,6 +41,7 @@ struct RowOptParams {
     const int32_t *map[2];
     float cfront[2], cback[2];
     int V[2], ntiles[2], Kd[2];
+    int F0;                 // column tile height (256 or 1024 rows)
     int64_t s[2], O[2];
     const float *x;
     float *out;
@@ -48,6 +49,10 @@ struct RowOptParams {
     const cf *tw;           // exp(-2 pi i j / 1024), j < 1024
     const cf *twr;          // exp(-2 pi i k / 2048), k <= 512
     int64_t nwork;
+    // L2-resident batching: when batch != 0 the launch covers tiles (t0 = b_t0, t1 in [b_t1, b_t1 + b_nt1)) only and the
+    // workspace holds just those tiles (tile slot = t1 - b_t1); row_inv covers output rows [b_o0, b_o0 + b_no0)
+    int batch, b_t0, b_t1, b_nt1;
+    int64_t b_o0, b_no0;
 };
 
 // s_tw[k1*32 + t] = W_1024^{t k1}
@@ -69,12 +74,14 @@ __global__ void __launch_bounds__(128, 4) row_fwd_packed(const __grid_constant__
     cf *sb = s_buf[warp];
     const int src_lane = (32 - lane) & 31;
     for (int64_t w = (int64_t)blockIdx.x * 4 + warp; w < p.nwork; w += (int64_t)gridDim.x * 4) {
-        const int64_t tile = w / kF0;
-        const int r = (int)(w % kF0);
-        const int t0 = (int)(tile / p.ntiles[1]), t1 = (int)(tile % p.ntiles[1]);
+        int64_t tile = w / p.F0;
+        const int r = (int)(w % p.F0);
+        int t0, t1;
+        if (p.batch) { t0 = p.b_t0; t1 = p.b_t1 + (int)tile; }
+        else { t0 = (int)(tile / p.ntiles[1]); t1 = (int)(tile % p.ntiles[1]); }
         const int64_t c0 = (int64_t)t0 * p.V[0] + r;         // padded row
         const int64_t cl0 = (int64_t)t1 * p.V[1];            // first padded column of the tile
-        float4 *dst = reinterpret_cast<float4 *>(p.ws + tile * ((int64_t)kF0 * kL) + (int64_t)r * kL);
+        float4 *dst = reinterpret_cast<float4 *>(p.ws + tile * ((int64_t)p.F0 * kL) + (int64_t)r * kL);
         // resolve the row (axis 0)
         bool zero_row = false, row_const = false, row_init = false;
         float row_cval = 0.f;
@@ -168,13 +175,15 @@ __global__ void __launch_bounds__(128, 4) row_inv_packed(const __grid_constant__
     const int src_lane = (32 - lane) & 31;
     const int ntl = p.ntiles[1];
     for (int64_t w = (int64_t)blockIdx.x * 4 + warp; w < p.nwork; w += (int64_t)gridDim.x * 4) {
-        const int t1 = (int)(w % ntl);
-        const int64_t o0 = w / ntl;
+        int t1;
+        int64_t o0;
+        if (p.batch) { t1 = p.b_t1 + (int)(w % p.b_nt1); o0 = p.b_o0 + w / p.b_nt1; }
+        else { t1 = (int)(w % ntl); o0 = w / ntl; }
         const int64_t q0 = o0 * p.s[0];
         const int64_t t0 = q0 / p.V[0];
         const int r0 = (int)(q0 - t0 * p.V[0]) + p.Kd[0] - 1;
-        const int64_t tile = t0 * ntl + t1;
-        const float4 *src = reinterpret_cast<const float4 *>(p.ws + tile * ((int64_t)kF0 * kL) + (int64_t)r0 * kL);
+        const int64_t tile = p.batch ? (int64_t)(t1 - p.b_t1) : t0 * ntl + t1;
+        const float4 *src = reinterpret_cast<const float4 *>(p.ws + tile * ((int64_t)p.F0 * kL) + (int64_t)r0 * kL);
         cf v[32], b[16];
 #pragma unroll
         for (int k2 = 0; k2 < 16; k2++) {
@@ -255,47 +264,54 @@ struct ColOptParams {
     int64_t nwork;          // ntiles_total * (kL / 8)
 };
 
-constexpr int kColPitch = 32 * 8 + 8;   // padded k1-row stride of the exchange buffer (complex elements)
-constexpr int kColSmem = (1024 + 32 * kColPitch) * 8;
+// R = 32: 1024-row tiles (256 threads); R = 16: 256-row tiles (128 threads).  F0 = R*R, radix R x radix R.
+template <int R> struct ColCfg {
+    static constexpr int F0 = R * R;
+    static constexpr int threads = R * 8;
+    static constexpr int pitch = R * 8 + 8;                         // padded k1-row stride of the exchange buffer (complex elements)
+    static constexpr int smem = (F0 + R * pitch) * 8;
+};
 
-__global__ void __launch_bounds__(256, 2) col_fmi(const __grid_constant__ ColOptParams p)
+template <int R>
+__global__ void __launch_bounds__(ColCfg<R>::threads, R == 32 ? 2 : 6) col_fmi(const __grid_constant__ ColOptParams p)
 {
+    constexpr int F0 = ColCfg<R>::F0, pitch = ColCfg<R>::pitch;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    cf *s_tw = reinterpret_cast<cf *>(smem_raw);        // 1024
-    cf *S = s_tw + 1024;                                // 32 * kColPitch
+    cf *s_tw = reinterpret_cast<cf *>(smem_raw);        // F0 entries: s_tw[k1*R + i] = W_F0^{i k1}
+    cf *S = s_tw + F0;                                  // R * pitch
     const int tid = threadIdx.x;
     const int c = tid & 7, i = tid >> 3;
-    load_tw_table(s_tw, p.tw, tid, blockDim.x);
+    for (int idx = tid; idx < F0; idx += blockDim.x) s_tw[idx] = p.tw[(idx / R) * (idx % R)];
     __syncthreads();
     for (int64_t w = blockIdx.x; w < p.nwork; w += gridDim.x) {
         const int cb = (int)(w % (kL / 8));
         const int64_t tile = w / (kL / 8);
-        cf *g = p.ws + tile * ((int64_t)kF0 * kL) + cb * 8 + c;
-        cf v[32];
+        cf *g = p.ws + tile * ((int64_t)F0 * kL) + cb * 8 + c;
+        cf v[R];
 #pragma unroll
-        for (int j = 0; j < 32; j++) v[j] = ld_cf(g + (int64_t)(i + 32 * j) * kL);
-        // ---- forward: radix 32 over j, twiddle, exchange, radix 32 over i ----
-        dft32<float>(v, false);
+        for (int j = 0; j < R; j++) v[j] = ld_cf(g + (int64_t)(i + R * j) * kL);
+        // ---- forward: radix R over j, twiddle, exchange, radix R over i ----
+        dft<float, R>(v, false);
 #pragma unroll
-        for (int k1 = 0; k1 < 32; k1++) S[k1 * kColPitch + i * 8 + c] = cmul(v[k1], s_tw[k1 * 32 + i]);
+        for (int k1 = 0; k1 < R; k1++) S[k1 * pitch + i * 8 + c] = cmul(v[k1], s_tw[k1 * R + i]);
         __syncthreads();
 #pragma unroll
-        for (int ii = 0; ii < 32; ii++) v[ii] = S[i * kColPitch + ii * 8 + c];
-        dft32<float>(v, false);                            // v[k2] = Xhat[q = i + 32 k2][column]
-        // ---- multiply by the kernel spectrum (rows q = i + 32 k2 stay in this thread for the inverse) ----
+        for (int ii = 0; ii < R; ii++) v[ii] = S[i * pitch + ii * 8 + c];
+        dft<float, R>(v, false);                           // v[k2] = Xhat[q = i + R k2][column]
+        // ---- multiply by the kernel spectrum (rows q = i + R k2 stay in this thread for the inverse) ----
         const cf *kp = p.kphys + cb * 8 + c;
         if (cb == 0) {
             // physical column 0 = DC + i Nyquist of every row: separate the two real sequences through the q <-> -q mirror
             __syncthreads();
             if (c == 0) {
 #pragma unroll
-                for (int k2 = 0; k2 < 32; k2++) S[i + 32 * k2] = v[k2];
+                for (int k2 = 0; k2 < R; k2++) S[i + R * k2] = v[k2];
             }
             __syncthreads();
             if (c == 0) {
 #pragma unroll
-                for (int k2 = 0; k2 < 32; k2++) {
-                    const int q = i + 32 * k2, qm = (kF0 - q) & (kF0 - 1);
+                for (int k2 = 0; k2 < R; k2++) {
+                    const int q = i + R * k2, qm = (F0 - q) & (F0 - 1);
                     const cf a = v[k2], b = S[qm];
                     const cf A = cf{0.5f * (a.re + b.re), 0.5f * (a.im - b.im)};      // spectrum of the DC column
                     const cf B = cf{0.5f * (a.im + b.im), -0.5f * (a.re - b.re)};     // spectrum of the Nyquist column
@@ -305,23 +321,23 @@ __global__ void __launch_bounds__(256, 2) col_fmi(const __grid_constant__ ColOpt
                 }
             } else {
 #pragma unroll
-                for (int k2 = 0; k2 < 32; k2++) v[k2] = cmul(v[k2], ld_cf(kp + (int64_t)(i + 32 * k2) * kKphysPitch));
+                for (int k2 = 0; k2 < R; k2++) v[k2] = cmul(v[k2], ld_cf(kp + (int64_t)(i + R * k2) * kKphysPitch));
             }
         } else {
 #pragma unroll
-            for (int k2 = 0; k2 < 32; k2++) v[k2] = cmul(v[k2], ld_cf(kp + (int64_t)(i + 32 * k2) * kKphysPitch));
+            for (int k2 = 0; k2 < R; k2++) v[k2] = cmul(v[k2], ld_cf(kp + (int64_t)(i + R * k2) * kKphysPitch));
         }
-        // ---- inverse: radix 32 over the register index, conj twiddle, exchange, radix 32 over i ----
-        dft32<float>(v, true);
+        // ---- inverse: radix R over the register index, conj twiddle, exchange, radix R over i ----
+        dft<float, R>(v, true);
         __syncthreads();                                   // every thread has finished reading S
 #pragma unroll
-        for (int n1 = 0; n1 < 32; n1++) S[n1 * kColPitch + i * 8 + c] = cmulc(v[n1], s_tw[n1 * 32 + i]);
+        for (int n1 = 0; n1 < R; n1++) S[n1 * pitch + i * 8 + c] = cmulc(v[n1], s_tw[n1 * R + i]);
         __syncthreads();
 #pragma unroll
-        for (int ii = 0; ii < 32; ii++) v[ii] = S[i * kColPitch + ii * 8 + c];
-        dft32<float>(v, true);
+        for (int ii = 0; ii < R; ii++) v[ii] = S[i * pitch + ii * 8 + c];
+        dft<float, R>(v, true);
 #pragma unroll
-        for (int n2 = 0; n2 < 32; n2++) st_cf(g + (int64_t)(i + 32 * n2) * kL, v[n2]);
+        for (int n2 = 0; n2 < R; n2++) st_cf(g + (int64_t)(i + R * n2) * kL, v[n2]);
         __syncthreads();                                   // S is rewritten by the next work item
     }
 }

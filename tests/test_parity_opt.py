@@ -15,6 +15,10 @@ CASES = [
     ((2100, 4200), (7, 3), 1, ("custom", [3, 5], [2, 3]), "replicate", True),
     ((1025, 2049), (63, 63), 1, "valid", "zeros", True),
     ((900, 5000), (3, 31), 3, ("explicit", [[0, 7], [40, 2]], [1, 1]), ("explicit", [["zeros", "reflect"], ["circular", "replicate"]]), True),
+    # 256-row column tiles (radix 16 x 16)
+    ((200, 5000), (11, 31), 2, "same", ("custom", ["reflect", "circular"]), True),          # BASELINE configs[1]
+    ((130, 1300), (3, 5), 1, "full", "replicate", False),
+    ((470, 1500), (9, 4), 1, ("custom", [4, 0], [3, 2]), ("const", -0.5), True),             # two 256-row tiles, strided output
 ]
 
 
