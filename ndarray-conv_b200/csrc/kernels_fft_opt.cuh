@@ -61,70 +61,126 @@ __device__ __forceinline__ void load_tw_table(cf *s_tw, const cf *tw, int tid, i
     for (int idx = tid; idx < 1024; idx += nt) s_tw[idx] = tw[(idx >> 5) * (idx & 31)];
 }
 
+// ---- cp.async helpers (LDGSTS): global -> shared without staging in registers ---------------------------------
+__device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 // ---- row forward -----------------------------------------------------------------------------------
+struct RowFwdInfo {
+    float4 *dst;
+    const float *src;       // interior rows: first sample of the tile
+    int64_t rowbase, cl0;
+    float row_cval;
+    bool zero_row, row_const, row_init, interior, vec;
+};
+
+__device__ __forceinline__ RowFwdInfo row_fwd_resolve(const RowOptParams &p, int64_t w)
+{
+    RowFwdInfo ri;
+    int64_t tile = w / p.F0;
+    const int r = (int)(w % p.F0);
+    int t0, t1;
+    if (p.batch) { t0 = p.b_t0; t1 = p.b_t1 + (int)tile; }
+    else { t0 = (int)(tile / p.ntiles[1]); t1 = (int)(tile % p.ntiles[1]); }
+    const int64_t c0 = (int64_t)t0 * p.V[0] + r;         // padded row
+    ri.cl0 = (int64_t)t1 * p.V[1];                       // first padded column of the tile
+    ri.dst = reinterpret_cast<float4 *>(p.ws + tile * ((int64_t)p.F0 * kL) + (int64_t)r * kL);
+    ri.zero_row = false; ri.row_const = false; ri.row_init = false; ri.row_cval = 0.f; ri.rowbase = 0;
+    if (c0 >= p.P[0]) ri.zero_row = true;
+    else {
+        const int32_t m0 = p.map[0][c0];
+        if (m0 >= 0) ri.rowbase = (int64_t)m0 * p.xstr[0];
+        else if (m0 == NDC_MAP_INIT) ri.row_init = true;
+        else { ri.row_const = true; ri.row_cval = (m0 == NDC_MAP_CONST_FRONT) ? p.cfront[0] : p.cback[0]; }
+    }
+    ri.interior = !ri.zero_row && !ri.row_const && !ri.row_init && p.xstr[1] == 1 && ri.cl0 >= p.pf[1] && ri.cl0 + kF1 <= p.pf[1] + p.n[1];
+    ri.src = p.x + ri.rowbase + (ri.cl0 - p.pf[1]);
+    ri.vec = ri.interior && (reinterpret_cast<uintptr_t>(ri.src) & 7) == 0;
+    return ri;
+}
+
+// Measured on B200 (c5): staging the next input row with 8-byte cp.async costs more issue slots than the latency it hides
+// (1.97 -> 2.06 ms), while the 16-byte variant in row_inv_packed pays off (2.01 -> 1.83 ms).  Input rows are only 8-byte
+// aligned in general ((cl0 - pf) * 4), so row_fwd keeps the direct register loads.
+constexpr bool kRowFwdPrefetch = false;
+
 __global__ void __launch_bounds__(128, 4) row_fwd_packed(const __grid_constant__ RowOptParams p)
 {
     __shared__ cf s_tw[1024];
     __shared__ cf s_twr[512];
-    __shared__ cf s_buf[4][32 * 33];
+    __shared__ __align__(16) cf s_buf[4][32 * 33];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     load_tw_table(s_tw, p.tw, threadIdx.x, blockDim.x);
     for (int idx = threadIdx.x; idx < 512; idx += blockDim.x) s_twr[idx] = p.twr[idx];
     __syncthreads();
     cf *sb = s_buf[warp];
     const int src_lane = (32 - lane) & 31;
-    for (int64_t w = (int64_t)blockIdx.x * 4 + warp; w < p.nwork; w += (int64_t)gridDim.x * 4) {
-        int64_t tile = w / p.F0;
-        const int r = (int)(w % p.F0);
-        int t0, t1;
-        if (p.batch) { t0 = p.b_t0; t1 = p.b_t1 + (int)tile; }
-        else { t0 = (int)(tile / p.ntiles[1]); t1 = (int)(tile % p.ntiles[1]); }
-        const int64_t c0 = (int64_t)t0 * p.V[0] + r;         // padded row
-        const int64_t cl0 = (int64_t)t1 * p.V[1];            // first padded column of the tile
-        float4 *dst = reinterpret_cast<float4 *>(p.ws + tile * ((int64_t)p.F0 * kL) + (int64_t)r * kL);
-        // resolve the row (axis 0)
-        bool zero_row = false, row_const = false, row_init = false;
-        float row_cval = 0.f;
-        int64_t rowbase = 0;
-        if (c0 >= p.P[0]) zero_row = true;
-        else {
-            const int32_t m0 = p.map[0][c0];
-            if (m0 >= 0) rowbase = (int64_t)m0 * p.xstr[0];
-            else if (m0 == NDC_MAP_INIT) row_init = true;
-            else { row_const = true; row_cval = (m0 == NDC_MAP_CONST_FRONT) ? p.cfront[0] : p.cback[0]; }
-        }
-        if (zero_row) {
+    const int64_t wstride = (int64_t)gridDim.x * 4;
+    int64_t w = (int64_t)blockIdx.x * 4 + warp;
+    if (w >= p.nwork) return;
+    RowFwdInfo cur = row_fwd_resolve(p, w);
+    // software pipeline: the NEXT row's 8 KB are copied global -> shared (cp.async, no registers) while this row computes
+    bool staged = false;
+    if (kRowFwdPrefetch && cur.vec) {
 #pragma unroll
-            for (int k2 = 0; k2 < 16; k2++) dst[lane + 32 * k2] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int j = 0; j < 32; j++) cp_async8(sb + lane + 32 * j, reinterpret_cast<const float2 *>(cur.src) + lane + 32 * j);
+        cp_async_commit();
+        staged = true;
+    }
+    for (; w < p.nwork; w += wstride) {
+        const bool has_next = kRowFwdPrefetch && (w + wstride < p.nwork);
+        RowFwdInfo nxt = cur;
+        if (has_next) nxt = row_fwd_resolve(p, w + wstride);
+        if (cur.zero_row) {
+#pragma unroll
+            for (int k2 = 0; k2 < 16; k2++) cur.dst[lane + 32 * k2] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (kRowFwdPrefetch && has_next && nxt.vec) {          // nothing staged for a zero row: the buffer is free
+#pragma unroll
+                for (int j = 0; j < 32; j++) cp_async8(sb + lane + 32 * j, reinterpret_cast<const float2 *>(nxt.src) + lane + 32 * j);
+                cp_async_commit();
+                staged = true;
+            }
+            if (kRowFwdPrefetch) cur = nxt; else if (w + wstride < p.nwork) cur = row_fwd_resolve(p, w + wstride);
             continue;
         }
         cf v[32];
-        const bool interior = !row_const && !row_init && p.xstr[1] == 1 && cl0 >= p.pf[1] && cl0 + kF1 <= p.pf[1] + p.n[1];
-        if (interior) {
-            const float *src = p.x + rowbase + (cl0 - p.pf[1]);
-            if ((reinterpret_cast<uintptr_t>(src) & 7) == 0) {
-                const float2 *s2 = reinterpret_cast<const float2 *>(src);
+        if (staged) {
+            cp_async_wait_all();
+            __syncwarp();
 #pragma unroll
-                for (int j = 0; j < 32; j++) { float2 t = __ldg(s2 + lane + 32 * j); v[j] = cf{t.x, t.y}; }
-            } else {
+            for (int j = 0; j < 32; j++) v[j] = sb[lane + 32 * j];
+            __syncwarp();
+            staged = false;
+        } else if (cur.vec) {
+            const float2 *s2 = reinterpret_cast<const float2 *>(cur.src);
 #pragma unroll
-                for (int j = 0; j < 32; j++) { const int e = 2 * (lane + 32 * j); v[j] = cf{__ldg(src + e), __ldg(src + e + 1)}; }
-            }
+            for (int j = 0; j < 32; j++) { float2 t = __ldg(s2 + lane + 32 * j); v[j] = cf{t.x, t.y}; }
+        } else if (cur.interior) {
+#pragma unroll
+            for (int j = 0; j < 32; j++) { const int e = 2 * (lane + 32 * j); v[j] = cf{__ldg(cur.src + e), __ldg(cur.src + e + 1)}; }
         } else {
 #pragma unroll
             for (int j = 0; j < 32; j++) {
                 float q[2];
 #pragma unroll
                 for (int h = 0; h < 2; h++) {
-                    const int64_t cl = cl0 + 2 * (lane + 32 * j) + h;
+                    const int64_t cl = cur.cl0 + 2 * (lane + 32 * j) + h;
                     float val = 0.f;
                     if (cl < p.P[1]) {
                         const int32_t m = p.map[1][cl];
                         if (m == NDC_MAP_CONST_FRONT) val = p.cfront[1];
                         else if (m == NDC_MAP_CONST_BACK) val = p.cback[1];
-                        else if (row_const) val = row_cval;
-                        else if (m == NDC_MAP_INIT || row_init) val = 0.f;
-                        else val = __ldg(p.x + rowbase + (int64_t)m * p.xstr[1]);
+                        else if (cur.row_const) val = cur.row_cval;
+                        else if (m == NDC_MAP_INIT || cur.row_init) val = 0.f;
+                        else val = __ldg(p.x + cur.rowbase + (int64_t)m * p.xstr[1]);
                     }
                     q[h] = val;
                 }
@@ -138,9 +194,16 @@ __global__ void __launch_bounds__(128, 4) row_fwd_packed(const __grid_constant__
 #pragma unroll
         for (int i = 0; i < 32; i++) v[i] = sb[lane * 33 + i];
         __syncwarp();
+        if (kRowFwdPrefetch && has_next && nxt.vec) {            // the buffer is free again: prefetch the next row
+#pragma unroll
+            for (int j = 0; j < 32; j++) cp_async8(sb + lane + 32 * j, reinterpret_cast<const float2 *>(nxt.src) + lane + 32 * j);
+            cp_async_commit();
+            staged = true;
+        }
         dft32<float>(v, false);                                  // over t -> k2: v[k2] = Z[lane + 32 k2]
         // Z[L-k] lives in lane (32-lane)&31, register 31-k2 (lane 0: register 32-k2; k = 0 pairs with L/2).
         // R2C post-processing: E = (Z[k] + conj Z[L-k])/2, O = -i (Z[k] - conj Z[L-k])/2, X[k] = E + w^k O, X[L-k] = conj(E - w^k O)
+        float4 *dst = cur.dst;
 #pragma unroll
         for (int k2 = 0; k2 < 16; k2++) {
             float px = __shfl_sync(0xffffffffu, v[31 - k2].re, src_lane);
@@ -158,36 +221,50 @@ __global__ void __launch_bounds__(128, 4) row_fwd_packed(const __grid_constant__
             }
             dst[lane + 32 * k2] = o4;
         }
+        if (kRowFwdPrefetch) cur = nxt; else if (w + wstride < p.nwork) cur = row_fwd_resolve(p, w + wstride);
     }
 }
 
 // ---- row inverse + crop + decimate ---------------------------------------------------------------------
+__device__ __forceinline__ const float4 *row_inv_src(const RowOptParams &p, int64_t w, int &t1, int64_t &o0)
+{
+    const int ntl = p.ntiles[1];
+    if (p.batch) { t1 = p.b_t1 + (int)(w % p.b_nt1); o0 = p.b_o0 + w / p.b_nt1; }
+    else { t1 = (int)(w % ntl); o0 = w / ntl; }
+    const int64_t q0 = o0 * p.s[0];
+    const int64_t t0 = q0 / p.V[0];
+    const int r0 = (int)(q0 - t0 * p.V[0]) + p.Kd[0] - 1;
+    const int64_t tile = p.batch ? (int64_t)(t1 - p.b_t1) : t0 * ntl + t1;
+    return reinterpret_cast<const float4 *>(p.ws + tile * ((int64_t)p.F0 * kL) + (int64_t)r0 * kL);
+}
+
 __global__ void __launch_bounds__(128, 4) row_inv_packed(const __grid_constant__ RowOptParams p)
 {
     __shared__ cf s_tw[1024];
     __shared__ cf s_twr[512];
-    __shared__ cf s_buf[4][32 * 33];
+    __shared__ __align__(16) cf s_buf[4][32 * 33];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     load_tw_table(s_tw, p.tw, threadIdx.x, blockDim.x);
     for (int idx = threadIdx.x; idx < 512; idx += blockDim.x) s_twr[idx] = p.twr[idx];
     __syncthreads();
     cf *sb = s_buf[warp];
+    float4 *sb4 = reinterpret_cast<float4 *>(sb);
     const int src_lane = (32 - lane) & 31;
-    const int ntl = p.ntiles[1];
-    for (int64_t w = (int64_t)blockIdx.x * 4 + warp; w < p.nwork; w += (int64_t)gridDim.x * 4) {
-        int t1;
-        int64_t o0;
-        if (p.batch) { t1 = p.b_t1 + (int)(w % p.b_nt1); o0 = p.b_o0 + w / p.b_nt1; }
-        else { t1 = (int)(w % ntl); o0 = w / ntl; }
-        const int64_t q0 = o0 * p.s[0];
-        const int64_t t0 = q0 / p.V[0];
-        const int r0 = (int)(q0 - t0 * p.V[0]) + p.Kd[0] - 1;
-        const int64_t tile = p.batch ? (int64_t)(t1 - p.b_t1) : t0 * ntl + t1;
-        const float4 *src = reinterpret_cast<const float4 *>(p.ws + tile * ((int64_t)p.F0 * kL) + (int64_t)r0 * kL);
+    const int64_t wstride = (int64_t)gridDim.x * 4;
+    int64_t w = (int64_t)blockIdx.x * 4 + warp;
+    if (w >= p.nwork) return;
+    int t1; int64_t o0;
+    const float4 *src = row_inv_src(p, w, t1, o0);
+#pragma unroll
+    for (int k2 = 0; k2 < 16; k2++) cp_async16(sb4 + lane + 32 * k2, src + lane + 32 * k2);
+    cp_async_commit();
+    for (; w < p.nwork; w += wstride) {
         cf v[32], b[16];
+        cp_async_wait_all();
+        __syncwarp();
 #pragma unroll
         for (int k2 = 0; k2 < 16; k2++) {
-            const float4 t = src[lane + 32 * k2];
+            const float4 t = sb4[lane + 32 * k2];
             // C2R pre-processing (x2): Z[k] = E + i O, Z[L-k] = conj(E) + i conj(O), E = Y[k] + conj Y[L-k], O = conj(w^k) (Y[k] - conj Y[L-k])
             if (lane == 0 && k2 == 0) {
                 v[0] = cf{t.x + t.y, t.x - t.y};                                   // slot 0 = ((Y[0], Y[L]) packed, Y[L/2])
@@ -200,7 +277,8 @@ __global__ void __launch_bounds__(128, 4) row_inv_packed(const __grid_constant__
                 b[k2] = cf{E.re + O.im, -E.im + O.re};
             }
         }
-        // v[j'] for j' >= 16 is Zy[lane + 32 j'] = the partner half loaded by lane (32-lane)&31 at index 31-j'
+        __syncwarp();
+        // v[j'] for j' >= 16 is Z[lane + 32 j'] = the partner half held by lane (32-lane)&31 at index 31-j'
 #pragma unroll
         for (int jp = 16; jp < 32; jp++) {
             float px = __shfl_sync(0xffffffffu, b[31 - jp].re, src_lane);
@@ -215,11 +293,20 @@ __global__ void __launch_bounds__(128, 4) row_inv_packed(const __grid_constant__
 #pragma unroll
         for (int i = 0; i < 32; i++) v[i] = sb[lane * 33 + i];
         __syncwarp();
+        // crop parameters of THIS row, then prefetch the next row's spectrum into the (free again) buffer
+        const int cur_t1 = t1;
+        const int64_t cur_o0 = o0;
+        if (w + wstride < p.nwork) {
+            src = row_inv_src(p, w + wstride, t1, o0);
+#pragma unroll
+            for (int k2 = 0; k2 < 16; k2++) cp_async16(sb4 + lane + 32 * k2, src + lane + 32 * k2);
+            cp_async_commit();
+        }
         dft32<float>(v, true);                                   // v[n2] = z[lane + 32 n2] = (y[2n], y[2n+1])
         // crop [Kd-1, F1) of the tile; global position m = t1*V + i; keep m < P and (m-Kd+1) % s == 0
         const int Kd1 = p.Kd[1];
-        const int64_t orow = o0 * p.O[1];
-        const int64_t mbase = (int64_t)t1 * p.V[1];
+        const int64_t orow = cur_o0 * p.O[1];
+        const int64_t mbase = (int64_t)cur_t1 * p.V[1];
         if (p.s[1] == 1) {
             const int64_t obase = orow + mbase - (Kd1 - 1);       // output element of local sample 0
             const bool vec_ok = (obase & 1) == 0;
