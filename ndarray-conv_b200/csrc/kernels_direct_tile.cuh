@@ -8,8 +8,10 @@
 //     (tools/exp/tma_probe.cu): with SWIZZLE_NONE the box must START on a 16-byte boundary of the innermost axis
 //     (coordinate * sizeof(T) % 16 == 0) or UTMALDG raises an illegal-instruction fault, so the box start is aligned
 //     down and the window is read with a per-tile shift;
-//   * every other edge tile (Const / Reflect / Replicate / Circular): a cooperative gather through the border index
-//     maps into the same layout -- the padded array of src/padding/mod.rs:84-117 is never materialised.
+//   * edge tiles with a non-zero border (Const / Reflect / Replicate / Circular): the same TMA load brings the in-bounds
+//     part; only the halo elements that fall outside the array are then patched through the border index maps
+//     (index arithmetic, a few % of the tile) -- the padded array of src/padding/mod.rs:84-117 is never materialised.
+//     Without TMA (1/2/16-byte elements, unaligned rows) the whole window is gathered through the maps.
 // The compacted tap list (gen_offset_list, src/dilation/mod.rs:34-60) lives in shared memory as (tile offset, weight);
 // each thread keeps TO0 accumulators in registers and walks the taps in the reference's order with un-fused
 // multiply/add, so results stay bit-identical (integers wrap, floats round identically).
@@ -77,19 +79,62 @@ __global__ void __launch_bounds__(kThreads) direct_tile_kernel(const __grid_cons
     const int t0 = tb;
     const int tt[3] = {t0, t1, t2};
     int64_t c_lo[3];
-    bool tma_ok = p.use_tma != 0;
+    const bool tma_ok = p.use_tma != 0;
+    bool need_patch = false;                                // the window overhangs a border that does not read as zero
 #pragma unroll
     for (int a = 0; a < 3; a++) {
         c_lo[a] = (int64_t)tt[a] * p.TO[a] * p.s[a];
         const int64_t hi = c_lo[a] + p.IT[a];               // the window the outputs of this tile actually read
-        if (c_lo[a] < p.pf[a] && !p.front_zero[a]) tma_ok = false;
-        if (hi > p.pf[a] + p.n[a] && !p.back_zero[a]) tma_ok = false;
+        if (c_lo[a] < p.pf[a] && !p.front_zero[a]) need_patch = true;
+        if (hi > p.pf[a] + p.n[a] && !p.back_zero[a]) need_patch = true;
     }
     // 16-byte alignment of the box start along the contiguous axis
     constexpr int kAlign = sizeof(T) >= 16 ? 1 : 16 / (int)sizeof(T);
     const int64_t cx2_raw = c_lo[2] - p.pf[2];
     const int shift2 = (int)(((cx2_raw % kAlign) + kAlign) % kAlign);
     const int row_elems = p.IT2p, plane_elems = p.IT[1] * p.IT2p;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int nrows = p.IT[0] * p.IT[1];
+    const int64_t c2_lo = c_lo[2] - shift2;
+
+    // value of the padded array along one tile row for i2 in [lo, hi): the two outer axes are resolved once per row
+    // (highest-numbered constant axis wins, never-written cells read 0), lanes sweep the contiguous axis
+    auto fill_row = [&](int row, int lo, int hi, int lo2, int hi2) {      // fills [lo,hi) and [lo2,hi2) of the row
+        const T *x = (const T *)p.x;
+        const int i0 = row / p.IT[1], i1 = row - i0 * p.IT[1];
+        const int64_t c0 = c_lo[0] + i0, c1 = c_lo[1] + i1;
+        T *trow = tile + row * row_elems;
+        bool zero = c0 >= p.P[0] || c1 >= p.P[1], has_const = false;
+        const unsigned char *cval = nullptr;
+        int64_t base = 0;
+        if (!zero) {
+            const int32_t m1 = p.map[1][c1];
+            if (m1 >= 0) base += (int64_t)m1 * p.xstr[1];
+            else if (m1 == NDC_MAP_INIT) zero = true;
+            else { has_const = true; cval = (m1 == NDC_MAP_CONST_FRONT) ? p.cfront[1] : p.cback[1]; }
+            if (!has_const) {
+                const int32_t m0 = p.map[0][c0];
+                if (m0 >= 0) base += (int64_t)m0 * p.xstr[0];
+                else if (m0 == NDC_MAP_INIT) zero = true;
+                else { has_const = true; cval = (m0 == NDC_MAP_CONST_FRONT) ? p.cfront[0] : p.cback[0]; }
+            }
+        }
+        const int n1 = hi - lo, ntot = n1 + (hi2 - lo2);
+#pragma unroll 2
+        for (int e = lane; e < ntot; e += 32) {
+            const int i2 = e < n1 ? lo + e : lo2 + (e - n1);
+            const int64_t c2 = c2_lo + i2;
+            T val = Elem<T>::zero();
+            if (c2 >= 0 && c2 < p.P[2] && !(c0 >= p.P[0] || c1 >= p.P[1])) {
+                const int32_t m2 = p.map[2][c2];
+                if (m2 == NDC_MAP_CONST_FRONT) val = *(const T *)p.cfront[2];
+                else if (m2 == NDC_MAP_CONST_BACK) val = *(const T *)p.cback[2];
+                else if (has_const) val = *(const T *)cval;
+                else if (m2 != NDC_MAP_INIT && !zero) val = x[base + (int64_t)m2 * p.xstr[2]];
+            }
+            trow[i2] = val;
+        }
+    };
 
     if (tma_ok) {
         if (tid == 0) {
@@ -106,11 +151,7 @@ __global__ void __launch_bounds__(kThreads) direct_tile_kernel(const __grid_cons
                 : "memory");
         }
     } else {
-        for (int idx = tid; idx < p.tile_elems; idx += kThreads) {
-            const int i2 = idx % row_elems, i1 = (idx / row_elems) % p.IT[1], i0 = idx / plane_elems;
-            const int64_t c[3] = {c_lo[0] + i0, c_lo[1] + i1, c_lo[2] - shift2 + i2};
-            tile[idx] = c[2] < 0 ? Elem<T>::zero() : tile_padded_at<T>(p, c);      // c[2] < 0: alignment slack, never read
-        }
+        for (int row = warp; row < nrows; row += kThreads / 32) fill_row(row, 0, row_elems, 0, 0);
     }
     // taps -> shared memory: (offset inside the tile, weight), reference order
     for (int t = tid; t < p.ntap; t += kThreads) {
@@ -132,6 +173,29 @@ __global__ void __launch_bounds__(kThreads) direct_tile_kernel(const __grid_cons
                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
                 "selp.u32 %0, 1, 0, p;\n\t}"
                 : "=r"(done) : "r"(mb), "r"(0u) : "memory");
+        }
+        if (need_patch) {
+            // halo patch.  (1) fringes: rows inside the array on the outer axes only leave it along axis 2 -- one thread per
+            // (row, fringe element), so the per-row map lookups run 32 rows at a time; (2) rows that lie outside the array on
+            // an outer axis are rebuilt whole, one warp per row.
+            const int f2 = (int)min((int64_t)row_elems, max((int64_t)0, p.pf[2] - c2_lo));                 // [0, f2) is front halo
+            const int b2 = (int)min((int64_t)row_elems, max((int64_t)0, p.pf[2] + p.n[2] - c2_lo));       // [b2, row_elems) is back halo
+            const int nh = f2 + (row_elems - b2);
+            for (int e = tid; e < nrows * nh; e += kThreads) {
+                const int row = e / nh, h = e - row * nh;
+                const int i2 = h < f2 ? h : b2 + (h - f2);
+                const int i0 = row / p.IT[1], i1 = row - i0 * p.IT[1];
+                const int64_t c[3] = {c_lo[0] + i0, c_lo[1] + i1, c2_lo + i2};
+                const bool outer = c[0] < p.pf[0] || c[0] >= p.pf[0] + p.n[0] || c[1] < p.pf[1] || c[1] >= p.pf[1] + p.n[1];
+                if (!outer) tile[row * row_elems + i2] = c[2] < 0 ? Elem<T>::zero() : tile_padded_at<T>(p, c);
+            }
+            for (int row = warp; row < nrows; row += kThreads / 32) {
+                const int i0 = row / p.IT[1], i1 = row - i0 * p.IT[1];
+                const int64_t c0 = c_lo[0] + i0, c1 = c_lo[1] + i1;
+                const bool outer = c0 < p.pf[0] || c0 >= p.pf[0] + p.n[0] || c1 < p.pf[1] || c1 >= p.pf[1] + p.n[1];
+                if (outer) fill_row(row, 0, row_elems, 0, 0);
+            }
+            __syncthreads();
         }
     }
     // compute: thread -> (o1, o2) of the tile, TO0 accumulators in registers

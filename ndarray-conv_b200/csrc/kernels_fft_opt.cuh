@@ -369,14 +369,30 @@ __global__ void __launch_bounds__(ColCfg<R>::threads, R == 32 ? 2 : 6) col_fmi(c
     const int tid = threadIdx.x;
     const int c = tid & 7, i = tid >> 3;
     for (int idx = tid; idx < F0; idx += blockDim.x) s_tw[idx] = p.tw[(idx / R) * (idx % R)];
-    __syncthreads();
+    // software pipeline: while the last inverse pass and the stores of one tile run, the exchange buffer is idle, so the next
+    // tile is copied into it (linear [F0][8]) with 16-byte cp.async -- 4 threads per 64-byte row segment, no registers held
+    constexpr int kChunks = F0 * 4 / ColCfg<R>::threads;       // 16-byte chunks per thread
+    auto prefetch = [&](int64_t wn) {
+        const int cbn = (int)(wn % (kL / 8));
+        const cf *gn = p.ws + (wn / (kL / 8)) * ((int64_t)F0 * kL) + cbn * 8;
+#pragma unroll
+        for (int m = 0; m < kChunks; m++) {
+            const int id = tid + ColCfg<R>::threads * m, row = id >> 2, part = id & 3;
+            cp_async16(S + row * 8 + part * 2, gn + (int64_t)row * kL + part * 2);
+        }
+        cp_async_commit();
+    };
+    if ((int64_t)blockIdx.x < p.nwork) prefetch(blockIdx.x);
     for (int64_t w = blockIdx.x; w < p.nwork; w += gridDim.x) {
         const int cb = (int)(w % (kL / 8));
         const int64_t tile = w / (kL / 8);
         cf *g = p.ws + tile * ((int64_t)F0 * kL) + cb * 8 + c;
         cf v[R];
+        cp_async_wait_all();
+        __syncthreads();                                   // the staged tile (and, first time, the twiddle table) is visible
 #pragma unroll
-        for (int j = 0; j < R; j++) v[j] = ld_cf(g + (int64_t)(i + R * j) * kL);
+        for (int j = 0; j < R; j++) v[j] = S[(i + R * j) * 8 + c];
+        __syncthreads();                                   // every thread has its rows: S becomes the exchange buffer
         // ---- forward: radix R over j, twiddle, exchange, radix R over i ----
         dft<float, R>(v, false);
 #pragma unroll
@@ -422,10 +438,11 @@ __global__ void __launch_bounds__(ColCfg<R>::threads, R == 32 ? 2 : 6) col_fmi(c
         __syncthreads();
 #pragma unroll
         for (int ii = 0; ii < R; ii++) v[ii] = S[i * pitch + ii * 8 + c];
+        __syncthreads();                                   // S is free: stage the next tile while this one finishes
+        if (w + gridDim.x < p.nwork) prefetch(w + gridDim.x);
         dft<float, R>(v, true);
 #pragma unroll
         for (int n2 = 0; n2 < R; n2++) st_cf(g + (int64_t)(i + R * n2) * kL, v[n2]);
-        __syncthreads();                                   // S is rewritten by the next work item
     }
 }
 
