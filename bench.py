@@ -269,7 +269,7 @@ def run_gpu(args, w, rank, world, local_rank):
         ms_step = ms_max / args.steps
         value = total_out / (ms_step * 1e-3) / 1e9
         compulsory = 4.0 * (n0 * n1 + kshape[0] * kshape[1] + total_out)      # SURVEY 8d alg_bytes (whole job)
-        roof = roofline_from_profile(kprof, args.steps, peak, peak_src)
+        roof = roofline_from_profile(kprof, args.steps, peak, peak_src, measured_traffic(args.workload) if world == 1 else None)
         cpu_v, cpu_t, cpu_s = cpu_sample(w, 1, 0, os.cpu_count() or 1) if world == 1 and not args.no_cpu else (None, None, None)
         line = {
             "metric": metric_name(), "value": value, "unit": "Gsamples/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -403,9 +403,18 @@ def read_profile(lib, proc):
     return out
 
 
-def roofline_from_profile(kprof, steps, peak, peak_src):
+def measured_traffic(workload):
+    """per-launch DRAM traffic of each kernel from the committed ncu capture (profiles/r01_traffic_<workload>.json)"""
+    p = ROOT / "profiles" / f"r01_traffic_{workload}.json"
+    if not p.exists():
+        return {}
+    return {k: v["traffic_bytes"] for k, v in json.loads(p.read_text())["kernels"].items()}
+
+
+def roofline_from_profile(kprof, steps, peak, peak_src, traffic=None):
     if not kprof:
         return None
+    traffic = traffic or {}
     top = max(kprof, key=lambda k: k["total_ms"])
     avg_ms = top["total_ms"] / max(top["launches"], 1)
     ach = top["alg_bytes_per_launch"] / (avg_ms * 1e-3) / 1e9
@@ -414,7 +423,9 @@ def roofline_from_profile(kprof, steps, peak, peak_src):
         k["avg_ms"] = a
         k["achieved_gbs"] = k["alg_bytes_per_launch"] / (a * 1e-3) / 1e9 if a > 0 else None
         k["frac_of_peak"] = k["achieved_gbs"] / peak if a > 0 else None
-    return {"bound": "hbm", "kernel": top["kernel"], "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+    for k in kprof:
+        k["traffic_bytes_ncu"] = traffic.get(k["kernel"])
+    return {"bound": "hbm", "kernel": top["kernel"], "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic.get(top["kernel"]),
             "peak_source": peak_src, "avg_launch_ms": avg_ms, "alg_bytes_per_launch": top["alg_bytes_per_launch"]}
 
 
