@@ -36,6 +36,9 @@ NDCONV_DTYPE(int8_t, NDCONV_I8) NDCONV_DTYPE(int16_t, NDCONV_I16) NDCONV_DTYPE(u
 NDCONV_DTYPE(uint32_t, NDCONV_U32) NDCONV_DTYPE(uint64_t, NDCONV_U64)
 #undef NDCONV_DTYPE
 
+template <class T> struct scalar_of { using type = T; static constexpr bool is_complex = false; };
+template <class R> struct scalar_of<std::complex<R>> { using type = R; static constexpr bool is_complex = true; };
+
 enum class ErrorKind { DataShape = 1, KernelShape = 2, MismatchShape = 3 };
 
 // Error<N>, src/lib.rs:148-159
@@ -149,8 +152,36 @@ public:
     FftProcessor(FftProcessor &&o) noexcept : p_(o.p_) { o.p_ = nullptr; }
     ndconv_processor *raw() { return p_; }
     int64_t launch_count() const { return ndconv_processor_launch_count(p_); }
+    // Processor::forward / backward (src/conv_fft/processor/mod.rs:91-118): unnormalised N-d FFT, spectrum with axis 0 moved to
+    // the end; backward divides by the element count and reuses the shape of the last forward (rp_origin_len).
+    template <class T, size_t N> Array<std::complex<typename scalar_of<T>::type>, N> forward(const Array<T, N> &x)
+    {
+        using C = std::complex<typename scalar_of<T>::type>;
+        constexpr bool cplx = scalar_of<T>::is_complex;
+        std::array<size_t, N> os{};
+        const size_t last = cplx ? x.shape[N - 1] : x.shape[N - 1] / 2 + 1;
+        if (N == 1) os[0] = last;
+        else { for (size_t i = 1; i + 1 < N; i++) os[i - 1] = x.shape[i]; os[N - 2] = last; os[N - 1] = x.shape[0]; }
+        Array<C, N> out(os);
+        int64_t shp[NDCONV_MAX_DIM];
+        origin_.assign(x.shape.begin(), x.shape.end());
+        for (size_t i = 0; i < N; i++) shp[i] = (int64_t)x.shape[i];
+        check(ndconv_fft_forward(p_, dtype_of<T>::value, (int)N, shp, x.data.data(), out.data.data(), NDCONV_MEM_HOST));
+        return out;
+    }
+    template <class T, size_t N> Array<T, N> backward(const Array<std::complex<typename scalar_of<T>::type>, N> &spectrum)
+    {
+        if (origin_.size() != N) throw Panic(NDCONV_ERR_BAD_ARG, "backward() before forward()");
+        std::array<size_t, N> s{};
+        int64_t shp[NDCONV_MAX_DIM];
+        for (size_t i = 0; i < N; i++) { s[i] = origin_[i]; shp[i] = (int64_t)origin_[i]; }
+        Array<T, N> out(s);
+        check(ndconv_fft_backward(p_, dtype_of<T>::value, (int)N, shp, spectrum.data.data(), out.data.data(), NDCONV_MEM_HOST));
+        return out;
+    }
 private:
     ndconv_processor *p_ = nullptr;
+    std::vector<size_t> origin_;
 };
 inline FftProcessor get_fft_processor(int device = 0) { return FftProcessor(device); }
 

@@ -83,7 +83,8 @@ EXPORTED_SYMBOLS = [
     "ndconv_border_index_map", "ndconv_processor_create", "ndconv_processor_destroy", "ndconv_processor_set_stream",
     "ndconv_processor_synchronize", "ndconv_processor_launch_count", "ndconv_processor_workspace_bytes",
     "ndconv_processor_set_profiling", "ndconv_processor_get_profile",
-    "ndconv_conv_direct", "ndconv_conv_fft", "ndconv_conv_fft_par", "ndconv_slab_plan", "ndconv_host_alloc", "ndconv_host_free",
+    "ndconv_conv_direct", "ndconv_conv_fft", "ndconv_conv_fft_par", "ndconv_fft_forward", "ndconv_fft_backward",
+    "ndconv_slab_plan", "ndconv_host_alloc", "ndconv_host_free",
 ]
 
 
@@ -119,6 +120,8 @@ class Library:
         c.ndconv_processor_get_profile.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
         for name in ("ndconv_conv_direct", "ndconv_conv_fft", "ndconv_conv_fft_par"):
             getattr(c, name).argtypes = [ctypes.c_void_p, ctypes.POINTER(_Problem), ctypes.c_void_p]
+        for name in ("ndconv_fft_forward", "ndconv_fft_backward"):
+            getattr(c, name).argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
         c.ndconv_slab_plan.argtypes = [ctypes.POINTER(_Problem), ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(_Slab)]
         c.ndconv_host_alloc.restype = ctypes.c_void_p
         c.ndconv_host_alloc.argtypes = [ctypes.c_size_t]
@@ -369,6 +372,31 @@ class Processor:
     @property
     def workspace_bytes(self):
         return int(self.lib.c.ndconv_processor_workspace_bytes(self.handle))
+
+    # Processor::forward / backward (src/conv_fft/processor/mod.rs:91-118) with the reference's rotated spectrum layout
+    def forward(self, x):
+        """N-d FFT of a real (f32/f64) or complex array; returns the spectrum with axis 0 moved to the end."""
+        x = np.ascontiguousarray(x)
+        cplx = np.iscomplexobj(x)
+        cdt = np.result_type(x.dtype, np.complex64)
+        last = x.shape[-1] if cplx else x.shape[-1] // 2 + 1
+        oshape = (list(x.shape[1:-1]) + [last, x.shape[0]]) if x.ndim > 1 else [last]
+        out = np.empty(oshape, cdt)
+        shp = (ctypes.c_int64 * x.ndim)(*x.shape)
+        self.lib.check(self.lib.c.ndconv_fft_forward(self.handle, DTYPE_CODES[x.dtype], x.ndim, shp, x.ctypes.data, out.ctypes.data, MEM_HOST))
+        self._origin = (x.shape, x.dtype)       # the reference's rp_origin_len: backward needs the real-space last-axis length
+        return out
+
+    def backward(self, spectrum, shape=None, dtype=None):
+        """inverse of forward (divides by the number of elements); shape / dtype default to those of the last forward()."""
+        if shape is None:
+            shape, dtype = self._origin
+        dtype = np.dtype(dtype)
+        spectrum = np.ascontiguousarray(spectrum, dtype=np.result_type(dtype, np.complex64))
+        out = np.empty(shape, dtype)
+        shp = (ctypes.c_int64 * len(shape))(*shape)
+        self.lib.check(self.lib.c.ndconv_fft_backward(self.handle, DTYPE_CODES[dtype], len(shape), shp, spectrum.ctypes.data, out.ctypes.data, MEM_HOST))
+        return out
 
     def close(self):
         if getattr(self, "handle", None):

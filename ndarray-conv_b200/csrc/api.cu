@@ -1134,6 +1134,98 @@ static int conv_fft_impl(ndconv_processor *p, const ndconv_problem *pr, void *ou
 }
 
 // ======================================================================================================
+// public N-d FFT of the processors: Processor::{forward, backward} (src/conv_fft/processor/mod.rs:91-118), with the
+// reference's rotated spectrum layout (real.rs:126-154, complex.rs:48-53): axis 0 ends up last.
+// Envelope of this build: {2,3,5,7}-smooth lengths that fit one shared-memory transform per axis.
+// ======================================================================================================
+template <class R>
+static int fft_nd_t(ndconv_processor *p, bool is_cx, int N, const int64_t *shape, const void *in, void *out, int memory, bool inverse)
+{
+    const bool is_dbl = sizeof(R) == 8;
+    int64_t total = 1;
+    for (int a = 0; a < N; a++) { if (shape[a] < 1) { set_error("fft: empty axis"); return NDCONV_ERR_DATA_SHAPE; } total *= shape[a]; }
+    FftPlan pl; pl.N = N; pl.is_cx = is_cx;
+    for (int a = 0; a < N; a++) {
+        const bool last = a == N - 1, real_axis = last && !is_cx;
+        const int cap = last ? cap_last_axis(is_cx, is_dbl) : cap_col_axis(is_dbl);
+        if (shape[a] > cap || (real_axis && (shape[a] & 1))) { set_error("fft: axis length outside this build's envelope (<= one shared-memory transform, even real axis)"); return NDCONV_ERR_UNSUPPORTED; }
+        pl.tl[a].F = (int)shape[a]; pl.tl[a].V = (int)shape[a]; pl.tl[a].ntiles = 1;
+        if (!factor_radices(real_axis ? (int)shape[a] / 2 : (int)shape[a], &pl.fl[a])) { set_error("fft: length is not {2,3,5,7}-smooth (Bluestein not implemented)"); return NDCONV_ERR_UNSUPPORTED; }
+    }
+    const int Fl = pl.tl[N - 1].F;
+    pl.H = is_cx ? Fl : Fl / 2 + 1;
+    pl.Hp = (int)align_up((size_t)pl.H, 16);
+    pl.rows_per_tile = 1;
+    for (int a = 0; a < N - 1; a++) pl.rows_per_tile *= pl.tl[a].F;
+    pl.tile_elems = pl.rows_per_tile * pl.Hp; pl.ntiles_total = 1;
+    const int es = (int)sizeof(R) * (is_cx ? 2 : 1);
+    const size_t real_bytes = (size_t)total * es, spec_elems = (size_t)(total / Fl) * pl.H, spec_bytes = spec_elems * sizeof(cx<R>);
+    int st = set_device(p); if (st) return st;
+    st = p->ws.reserve((size_t)pl.tile_elems * sizeof(cx<R>)); if (st) return st;
+    // identity border maps (no padding)
+    Geom g; g.ndim = N; g.es = es;
+    std::vector<int32_t> maps[NDC_MAX_DIM];
+    for (int a = 0; a < N; a++) { maps[a].resize((size_t)shape[a]); for (int64_t i = 0; i < shape[a]; i++) maps[a][(size_t)i] = (int32_t)i; }
+    MetaLayout ml;
+    st = upload_meta(p, p->kmeta, g, maps, nullptr, &ml); if (st) return st;
+    st = be_sync(p->stream); if (st) return st;
+    // staging for host callers
+    const void *dev_in = in; void *dev_out = out;
+    const size_t in_bytes = inverse ? spec_bytes : real_bytes, out_bytes = inverse ? real_bytes : spec_bytes;
+    if (memory == NDCONV_MEM_HOST) {
+        st = p->in_stage.reserve(in_bytes); if (st) return st;
+        st = p->out_stage.reserve(out_bytes); if (st) return st;
+        st = be_h2d(p->in_stage.p, in, in_bytes, p->stream); if (st) return st;
+        dev_in = p->in_stage.p; dev_out = p->out_stage.p;
+    }
+    RowParams<R> rp; memset(&rp, 0, sizeof(rp));
+    rp.ndim = N; rp.is_cx = is_cx ? 1 : 0;
+    int64_t xs = 1;
+    for (int a = N - 1; a >= 0; a--) {
+        rp.n[a] = shape[a]; rp.xstr[a] = xs; xs *= shape[a]; rp.P[a] = shape[a];
+        rp.map[a] = (const int32_t *)((const unsigned char *)p->kmeta.p + ml.map_off[a]);
+        rp.F[a] = pl.tl[a].F; rp.V[a] = pl.tl[a].F; rp.ntiles[a] = 1; rp.Kd[a] = 1; rp.s[a] = 1; rp.O[a] = shape[a];
+    }
+    rp.ws = (cx<R> *)p->ws.p; rp.H = pl.H; rp.Hp = pl.Hp; rp.rows_per_tile = pl.rows_per_tile; rp.tile_elems = pl.tile_elems;
+    st = fill_plan_dev<R>(p, pl.fl[N - 1], &rp.plan); if (st) return st;
+    if (!is_cx) { st = get_tw_r<R>(p, Fl, &rp.twr); if (st) return st; }
+    PermuteParams<R> pp; pp.n0 = N > 1 ? shape[0] : 1; pp.rest_rows = N > 1 ? pl.rows_per_tile / shape[0] : 1; pp.H = pl.H; pp.Hp = pl.Hp;
+    const int64_t pgrid = std::min<int64_t>((int64_t)(spec_elems + 255) / 256, (int64_t)p->num_sms * 16 * kMaxGridMult);
+    const double sb = (double)spec_bytes;
+    if (!inverse) {
+        rp.x = dev_in;
+        st = run_row<R>(p, 0, rp, 0, "fft_row_fwd", (double)real_bytes + sb); if (st) return st;
+        for (int a = N - 2; a >= 0; a--) { st = run_col<R>(p, pl, a, 0, rp.ws, nullptr, 1, "fft_col_fwd", 2 * sb); if (st) return st; }
+        pp.src = rp.ws; pp.dst = (cx<R> *)dev_out; pp.to_rotated = 1;
+        st = launch<PermuteBody<R>, PermuteParams<R>>(p->lc(), "fft_layout_rotate", 2 * sb, pgrid, 256, 0, pp); if (st) return st;
+    } else {
+        pp.src = (const cx<R> *)dev_in; pp.dst = rp.ws; pp.to_rotated = 0;
+        st = launch<PermuteBody<R>, PermuteParams<R>>(p->lc(), "fft_layout_rotate", 2 * sb, pgrid, 256, 0, pp); if (st) return st;
+        for (int a = 0; a <= N - 2; a++) { st = run_col<R>(p, pl, a, 1, rp.ws, nullptr, 1, "fft_col_inv", 2 * sb); if (st) return st; }
+        rp.out = dev_out; rp.scale = (R)(1.0L / (long double)total);            // real.rs:278-279, complex.rs:141-142
+        st = run_row<R>(p, 1, rp, pl.rows_per_tile, "fft_row_inv", (double)real_bytes + sb); if (st) return st;
+    }
+    if (memory == NDCONV_MEM_HOST) {
+        st = be_d2h(out, dev_out, out_bytes, p->stream); if (st) return st;
+        st = be_sync(p->stream); if (st) return st;
+    }
+    return NDCONV_OK;
+}
+
+static int fft_nd(ndconv_processor *p, int dtype, int ndim, const int64_t *shape, const void *in, void *out, int memory, bool inverse)
+{
+    if (!p || !shape || !in || !out || ndim < 1 || ndim > NDC_MAX_DIM) { set_error("fft: bad arguments"); return NDCONV_ERR_BAD_ARG; }
+    switch (dtype) {
+    case NDCONV_F32: return fft_nd_t<float>(p, false, ndim, shape, in, out, memory, inverse);
+    case NDCONV_F64: return fft_nd_t<double>(p, false, ndim, shape, in, out, memory, inverse);
+    case NDCONV_C32: return fft_nd_t<float>(p, true, ndim, shape, in, out, memory, inverse);
+    case NDCONV_C64: return fft_nd_t<double>(p, true, ndim, shape, in, out, memory, inverse);
+    }
+    set_error("fft: dtype must be f32/f64/Complex (integer FFT is documented as broken in the reference)");
+    return NDCONV_ERR_UNSUPPORTED;
+}
+
+// ======================================================================================================
 // C ABI
 // ======================================================================================================
 extern "C" {
@@ -1312,6 +1404,15 @@ static int with_processor(ndconv_processor *p, const ndconv_problem *pr, void *o
 int ndconv_conv_direct(ndconv_processor *p, const ndconv_problem *problem, void *out) { return with_processor(p, problem, out, conv_direct_impl); }
 int ndconv_conv_fft(ndconv_processor *p, const ndconv_problem *problem, void *out) { return with_processor(p, problem, out, conv_fft_impl); }
 int ndconv_conv_fft_par(ndconv_processor *p, const ndconv_problem *problem, void *out) { return with_processor(p, problem, out, conv_fft_impl); }
+
+int ndconv_fft_forward(ndconv_processor *p, int dtype, int ndim, const int64_t *shape, const void *in, void *out, int memory)
+{
+    return fft_nd(p, dtype, ndim, shape, in, out, memory, false);
+}
+int ndconv_fft_backward(ndconv_processor *p, int dtype, int ndim, const int64_t *shape, const void *spectrum, void *out, int memory)
+{
+    return fft_nd(p, dtype, ndim, shape, spectrum, out, memory, true);
+}
 
 int ndconv_slab_plan(const ndconv_problem *problem, int path, int n_slabs, int slab, ndconv_slab *out)
 {

@@ -207,6 +207,7 @@ template <class R> struct RowParams {
     int64_t rows_per_tile;      // prod_{a<N-1} F[a]
     int64_t tile_elems;         // rows_per_tile * Hp
     int64_t nwork;
+    R scale;                    // applied by the final store; 0 = none (conv_fft folds 1/len into the kernel spectrum)
 };
 
 template <class R> struct ColParams {
@@ -365,8 +366,9 @@ template <class R> HD void crop_store_row(const BlockCtx &c, const RowParams<R> 
         if (q % s) continue;
         const int64_t o = q / s;
         if (o >= p.O[a]) continue;
-        if (p.is_cx) ((cx<R> *)p.out)[orow_base[b] + o] = res[(size_t)b * zs + i];
-        else ((R *)p.out)[orow_base[b] + o] = ((const R *)(res + (size_t)b * zs))[i];
+        const R sc = p.scale != (R)0 ? p.scale : (R)1;
+        if (p.is_cx) { const cx<R> v = res[(size_t)b * zs + i]; ((cx<R> *)p.out)[orow_base[b] + o] = cx<R>{v.re * sc, v.im * sc}; }
+        else ((R *)p.out)[orow_base[b] + o] = ((const R *)(res + (size_t)b * zs))[i] * sc;
     }
 }
 
@@ -481,6 +483,28 @@ template <class R> struct ColBody {
             }
             for (int idx = c.tid; idx < F * W; idx += c.nt) g[(int64_t)(idx / W) * p.inner + idx % W] = res[idx];
             c.sync();
+        }
+    }
+};
+
+// ---- spectrum layout of the public processors -------------------------------------------------------
+// natural [n0][rest (pitch-padded last axis)]  <->  rotated [rest (dense)][n0]: "axis 0 moves to the end".
+template <class R> struct PermuteParams {
+    const cx<R> *src;
+    cx<R> *dst;
+    int64_t n0, rest_rows, H, Hp;     // rest = rest_rows x H valid bins, rows pitched by Hp on the natural side
+    int to_rotated;                   // 1: natural -> rotated, 0: rotated -> natural
+};
+template <class R> struct PermuteBody {
+    static HD void run(const BlockCtx &c, const PermuteParams<R> &p)
+    {
+        const int64_t total = p.n0 * p.rest_rows * p.H;
+        for (int64_t e = c.bid * c.nt + c.tid; e < total; e += c.nb * c.nt) {
+            const int64_t i0 = e % p.n0, rest = e / p.n0;          // rotated side is dense: (rest, i0), i0 fastest
+            const int64_t k = rest % p.H, rr = rest / p.H;
+            const int64_t nat = (i0 * p.rest_rows + rr) * p.Hp + k;
+            if (p.to_rotated) p.dst[e] = p.src[nat];
+            else p.dst[nat] = p.src[e];
         }
     }
 };

@@ -154,6 +154,17 @@ static void device_tests()
         }
         CHECK(proc.launch_count() > 0);
     });
+    run_test("processor::real::round_trip_2d (forward o backward = id, rotated layout [n1/2+1, n0])", [] {
+        Array<double, 2> x({6, 10});
+        for (size_t i = 0; i < x.len(); i++) x.data[i] = std::sin(0.37 * (double)i) + 0.01 * (double)i;
+        auto proc = get_fft_processor();
+        auto spec = proc.forward(x);
+        CHECK((spec.shape == std::array<size_t, 2>{6, 6}));          // [10/2+1, 6]
+        double dc = 0; for (double v : x.data) dc += v;
+        CHECK(std::abs(spec.data[0] - std::complex<double>(dc, 0)) < 1e-10);
+        auto back = proc.backward<double, 2>(spec);
+        for (size_t i = 0; i < x.len(); i++) CHECK(std::fabs(back.data[i] - x.data[i]) < 1e-10);
+    });
 }
 
 static void host_tests()
