@@ -16,7 +16,7 @@
 #include "host_logic.h"
 #include "kernels_direct.h"
 #include "kernels_fft.h"
-#include "kernels_fft_opt.cuh"
+#include "kernels_fft_fast.cuh"
 #include "kernels_direct_tile.cuh"
 
 #ifdef NDCONV_CUDA
@@ -335,17 +335,40 @@ struct FftPlan {
     int64_t rows_per_tile = 1, tile_elems = 0, ntiles_total = 1;
 };
 
-static bool opt2d_eligible(const Geom &g)
+// sm_100a fast path (kernels_fft_fast.cuh): real f32, rank 2 or 3, power-of-two overlap-save tiles
+static bool fast_eligible(const Geom &g)
 {
 #ifdef NDCONV_CUDA
     static const bool disabled = getenv("NDCONV_DISABLE_OPT") != nullptr;
-    if (disabled) return false;
-    static const int min_p0 = getenv("NDCONV_OPT_MIN_P0") ? atoi(getenv("NDCONV_OPT_MIN_P0")) : 64;
-    return g.ndim == 2 && g.dtype == NDCONV_F32 && g.P[0] >= min_p0 && g.P[1] >= 1200 && g.Kd[0] <= 512 && g.Kd[1] <= 1024;
+    if (disabled || g.dtype != NDCONV_F32 || (g.ndim != 2 && g.ndim != 3)) return false;
+    const int al = g.ndim - 1;
+    if (g.P[al] < 128 || g.Kd[al] > 1024) return false;
+    int64_t tot = 1;
+    for (int a = 0; a < g.ndim; a++) { tot *= g.P[a]; if (a < al && g.Kd[a] > 512) return false; }
+    if (tot < 16384) return false;
+    // the row kernels decode work indices in 32 bits: rows (tile overlap inflates by < 2x per axis) x last-axis tiles must fit
+    double work = (double)(g.P[al] / 128 + 2);
+    for (int a = 0; a < al; a++) work *= 2.0 * (double)g.P[a] + 16.0;
+    return work < 2.0e9;
 #else
     (void)g;
     return false;
 #endif
+}
+// tile length of one axis from a power-of-two menu: fewest transformed samples, ties to the longer tile
+static void fast_pick_tile(int64_t P, int64_t Kd, const int *menu, int nmenu, AxisTiling *out)
+{
+    for (int pass = 0; pass < 2 && out->F == 0; pass++) {        // pass 0: at least half of every tile useful; pass 1: anything that works
+        double best = 1e300;
+        for (int i = 0; i < nmenu; i++) {
+            const int F = menu[i];
+            const int64_t V = F - Kd + 1;
+            if (V < 1 || (pass == 0 && 2 * V < F)) continue;
+            const int64_t nt = (P - Kd + 1 + V - 1) / V;
+            const double c = (double)nt * F;
+            if (c <= best) { best = c; out->F = F; out->V = (int)V; out->ntiles = (int)nt; }
+        }
+    }
 }
 
 static int make_plan(const Geom &g, FftPlan *pl)
@@ -353,22 +376,15 @@ static int make_plan(const Geom &g, FftPlan *pl)
     const int N = g.ndim;
     const bool is_cx = dtype_is_complex(g.dtype), is_dbl = (g.dtype == NDCONV_F64 || g.dtype == NDCONV_C64);
     pl->N = N; pl->is_cx = is_cx;
-    pl->opt2d = opt2d_eligible(g);
+    pl->opt2d = fast_eligible(g);
     for (int a = 0; a < N; a++) {
         if (pl->opt2d) {
-            int F = 2048;
-            if (a == 0) {
-                // column tile height: 1024 (radix 32x32) or 256 (radix 16x16), whichever transforms fewer rows in total
-                F = 1024;
-                if (g.Kd[0] <= 128) {
-                    const int64_t M0 = g.P[0] - g.Kd[0] + 1;
-                    const int64_t c1024 = ((M0 + (1024 - g.Kd[0])) / (1024 - g.Kd[0] + 1)) * 1024, c256 = ((M0 + (256 - g.Kd[0])) / (256 - g.Kd[0] + 1)) * 256;
-                    if (c256 < c1024) F = 256;
-                }
-            }
-            pl->tl[a].F = F; pl->tl[a].V = F - (int)g.Kd[a] + 1;
-            pl->tl[a].ntiles = (int)((g.P[a] - g.Kd[a] + 1 + pl->tl[a].V - 1) / pl->tl[a].V);
-            if (!factor_radices(a == 0 ? F : F / 2, &pl->fl[a])) return NDCONV_ERR_INTERNAL;
+            static const int menu_last[4] = {256, 512, 1024, 2048}, menu_col[7] = {16, 32, 64, 128, 256, 512, 1024};
+            pl->tl[a].F = 0;
+            if (a == N - 1) fast_pick_tile(g.P[a], g.Kd[a], menu_last, 4, &pl->tl[a]);
+            else fast_pick_tile(g.P[a], g.Kd[a], menu_col, 7, &pl->tl[a]);
+            if (pl->tl[a].F == 0) { pl->opt2d = false; a = -1; continue; }      // no usable tile: replan everything on the generic path
+            if (!factor_radices(a == N - 1 ? pl->tl[a].F / 2 : pl->tl[a].F, &pl->fl[a])) return NDCONV_ERR_INTERNAL;
             continue;
         }
         const bool last = (a == N - 1);
@@ -678,10 +694,27 @@ static int conv_direct_impl(ndconv_processor *p, const ndconv_problem *pr, void 
     return NDCONV_OK;
 }
 
+static FastDiv make_fastdiv(int d)
+{
+    FastDiv f; f.d = d < 1 ? 1 : d;
+    int l = 0;
+    while ((1ll << l) < f.d) l++;
+    f.shift = 32 + l;
+    f.mul = (uint64_t)((((unsigned __int128)1 << f.shift) + (unsigned)f.d - 1) / (unsigned)f.d);     // ceil(2^shift / d): exact for n < 2^32
+    return f;
+}
+
 template <class R> static int fill_plan_dev(ndconv_processor *p, const FftLen &fl, FftPlanDev<R> *d)
 {
     d->L = fl.L; d->npass = fl.npass;
     for (int i = 0; i < NDC_MAX_PASS; i++) d->radix[i] = i < fl.npass ? fl.radix[i] : 1;
+    int ns = 1;
+    for (int i = 0; i < NDC_MAX_PASS; i++) {
+        const int r = d->radix[i];
+        d->by_m[i] = make_fastdiv(std::max(1, fl.L / r));
+        d->by_ns[i] = make_fastdiv(ns);
+        if (i < fl.npass) ns *= r;
+    }
     return get_tw_c<R>(p, fl.L, &d->tw);
 }
 
@@ -705,7 +738,9 @@ static int run_row(ndconv_processor *p, int kind /*0 fwd 1 inv 2 1d*/, RowParams
     const int L = rp.plan.L;
     if (kind == 2) rp.B = 1;
     else rp.B = pick_rows_per_block(L, csz);
-    size_t smem = 2 * (size_t)rp.B * (L + 1) * csz + (size_t)rp.B * 64 + 64;
+    size_t smem = align_up(2 * (size_t)rp.B * (L + 1) * csz + (size_t)rp.B * 64 + 64, 16);
+    rp.tw_smem_off = 0;
+    if (smem + (size_t)L * csz <= 160 * 1024 && L > 1) { rp.tw_smem_off = (int)smem; smem += (size_t)L * csz; }   // twiddle table copy
     if (smem > 227 * 1024) { set_error("internal: row kernel shared memory"); return NDCONV_ERR_INTERNAL; }
     int N = rp.ndim;
     int64_t ntiles_total = 1;
@@ -735,7 +770,9 @@ static int run_col(ndconv_processor *p, const FftPlan &pl, int axis, int mode, c
     while (W > 1 && 2 * (size_t)cp.F * W * sizeof(cx<R>) > kColSmemBudget) W >>= 1;
     cp.W = W;
     cp.nwork = ntiles_total * cp.outer * (cp.inner / W);
-    size_t smem = 2 * (size_t)cp.F * W * sizeof(cx<R>) + 64;
+    size_t smem = align_up(2 * (size_t)cp.F * W * sizeof(cx<R>) + 64, 16);
+    cp.tw_smem_off = 0;
+    if (cp.F > 1) { cp.tw_smem_off = (int)smem; smem += (size_t)cp.F * sizeof(cx<R>); }
     int block = pick_block_threads((int64_t)cp.F * W / 4);
     int64_t grid = std::min<int64_t>(cp.nwork, (int64_t)p->num_sms * 4 * kMaxGridMult);
     return launch<ColBody<R>, ColParams<R>>(p->lc(), name, alg_bytes, grid, block, smem, cp);
@@ -821,116 +858,113 @@ static int get_kernel_spectrum(ndconv_processor *p, const ndconv_problem *pr, co
 }
 
 #ifdef NDCONV_CUDA
-// sm_100a fast path: 2-D real f32, tiles 1024 x 2048 (kernels_fft_opt.cuh)
-static int conv_fft_opt2d(ndconv_processor *p, const ndconv_problem *pr, const Geom &g, const FftPlan &pl, const MetaLayout &ml, const DevBuf &metabuf,
-                          const void *dev_x, void *dev_out, KSpecEntry *ent)
+// sm_100a fast path: real f32, rank 2 / 3, power-of-two overlap-save tiles (kernels_fft_fast.cuh)
+template <int T, int N> static void launch_row_n(bool inverse, const fast::RowParams &rp, int grid, stream_t stm)
 {
-    using namespace ndc::opt;
-    int st;
-    const int F0 = pl.tl[0].F;                      // 1024 or 256
-    if (!ent->pair.p) {
-        st = ent->pair.reserve((size_t)F0 * kKphysPitch * sizeof(cf)); if (st) return st;
-        KphysParams kp; kp.kspec = (const cx<float> *)ent->buf.p; kp.kphys = (cx<float> *)ent->pair.p; kp.F0 = F0; kp.L = kL; kp.Hp = pl.Hp; kp.pitch = kKphysPitch;
-        st = launch<KphysBody, KphysParams>(p->lc(), "kspec_phys_repack", (double)F0 * kKphysPitch * 16, p->num_sms * 4, 256, 0, kp); if (st) return st;
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(fast::row_fwd<T, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, fast::RowCfg<T>::smem);
+        cudaFuncSetAttribute(fast::row_inv<T, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, fast::RowCfg<T>::smem);
+        attr = true;
     }
-    const int64_t tile_elems = (int64_t)F0 * kL;
-    {
-        const char *bt = getenv("NDCONV_BATCH_TILES");
-        const int64_t ws_tiles = (bt && atoi(bt) > 0) ? std::min<int64_t>(atoi(bt), pl.tl[1].ntiles) : pl.ntiles_total;
-        st = p->ws.reserve((size_t)ws_tiles * tile_elems * sizeof(cf)); if (st) return st;
+    if (inverse) fast::row_inv<T, N><<<grid, 128, fast::RowCfg<T>::smem, stm>>>(rp);
+    else fast::row_fwd<T, N><<<grid, 128, fast::RowCfg<T>::smem, stm>>>(rp);
+}
+template <int T> static void launch_row(bool inverse, const fast::RowParams &rp, int grid, stream_t stm)
+{
+    if (rp.ndim == 2) launch_row_n<T, 2>(inverse, rp, grid, stm);
+    else launch_row_n<T, 3>(inverse, rp, grid, stm);
+}
+template <int E, int Tc> static void launch_col_t(const fast::ColParams &cp, int num_sms, stream_t stm)
+{
+    using C = fast::ColCfg<E, Tc>;
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(fast::col_pass<E, Tc>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::smem); attr = true; }
+    const int per_sm = std::max(1, std::min(16, (int)((200 * 1024) / C::smem)));
+    const int grid = (int)std::min<int64_t>(cp.nwork, (int64_t)num_sms * std::max(C::min_blocks, std::min(per_sm, 2048 / C::threads)));
+    fast::col_pass<E, Tc><<<grid, C::threads, C::smem, stm>>>(cp);
+}
+static void launch_col(int F, const fast::ColParams &cp, int num_sms, stream_t stm)
+{
+    switch (F) {
+    case 1024: launch_col_t<32, 32>(cp, num_sms, stm); break;
+    case 512: launch_col_t<32, 16>(cp, num_sms, stm); break;
+    case 256: launch_col_t<16, 16>(cp, num_sms, stm); break;
+    case 128: launch_col_t<16, 8>(cp, num_sms, stm); break;
+    case 64: launch_col_t<8, 8>(cp, num_sms, stm); break;
+    case 32: launch_col_t<8, 4>(cp, num_sms, stm); break;
+    default: launch_col_t<8, 2>(cp, num_sms, stm); break;
     }
-    const cx<float> *tw = nullptr, *twr = nullptr;
-    const cx<float> *tw_col = nullptr;
-    st = get_tw_c<float>(p, kL, &tw); if (st) return st;
-    st = get_tw_c<float>(p, F0, &tw_col); if (st) return st;
-    st = get_tw_r<float>(p, kF1, &twr); if (st) return st;
+}
 
-    RowOptParams rp; memset(&rp, 0, sizeof(rp));
-    for (int a = 0; a < 2; a++) {
+static int conv_fft_fast(ndconv_processor *p, const ndconv_problem *pr, const Geom &g, const FftPlan &pl, const MetaLayout &ml, const DevBuf &metabuf,
+                         const void *dev_x, void *dev_out, KSpecEntry *ent)
+{
+    using namespace ndc::fast;
+    const int N = g.ndim, al = N - 1;
+    const int L = pl.tl[al].F / 2, pitch = L + kPad, T = L / 32;
+    int st;
+    int64_t rows_per_tile = 1;
+    for (int a = 0; a < al; a++) rows_per_tile *= pl.tl[a].F;
+    const int64_t tile_elems = rows_per_tile * pitch;
+    if (!ent->pair.p) {
+        st = ent->pair.reserve((size_t)tile_elems * sizeof(cf)); if (st) return st;
+        KfastParams kp; kp.kspec = (const cx<float> *)ent->buf.p; kp.kfast = (cx<float> *)ent->pair.p; kp.rows = rows_per_tile; kp.L = L; kp.Hp = pl.Hp;
+        st = launch<KfastBody, KfastParams>(p->lc(), "kspec_fast_layout", (double)tile_elems * 16, p->num_sms * 4, 256, 0, kp); if (st) return st;
+    }
+    st = p->ws.reserve((size_t)pl.ntiles_total * tile_elems * sizeof(cf)); if (st) return st;
+    const cx<float> *tw = nullptr, *twr = nullptr;
+    st = get_tw_c<float>(p, L, &tw); if (st) return st;
+    st = get_tw_r<float>(p, 2 * L, &twr); if (st) return st;
+
+    fast::RowParams rp; memset(&rp, 0, sizeof(rp));
+    rp.ndim = N;
+    for (int a = 0; a < N; a++) {
         rp.n[a] = g.n[a]; rp.xstr[a] = g.xstr[a]; rp.P[a] = g.P[a]; rp.pf[a] = g.pf[a];
         rp.map[a] = (const int32_t *)((const unsigned char *)metabuf.p + ml.map_off[a]);
-        rp.V[a] = pl.tl[a].V; rp.ntiles[a] = pl.tl[a].ntiles; rp.Kd[a] = (int)g.Kd[a]; rp.s[a] = g.s[a]; rp.O[a] = g.O[a];
+        rp.F[a] = pl.tl[a].F; rp.V[a] = pl.tl[a].V; rp.ntiles[a] = pl.tl[a].ntiles; rp.Kd[a] = (int)g.Kd[a]; rp.s[a] = g.s[a]; rp.O[a] = g.O[a];
         rp.cfront[a] = pr->border[a][0].type == NDCONV_BORDER_CONST ? *(const float *)pr->border[a][0].value : 0.f;
         rp.cback[a] = pr->border[a][1].type == NDCONV_BORDER_CONST ? *(const float *)pr->border[a][1].value : 0.f;
     }
-    rp.x = (const float *)dev_x; rp.out = (float *)dev_out; rp.ws = (cf *)p->ws.p; rp.tw = tw; rp.twr = twr; rp.F0 = F0;
-
-    static bool attr_set = false;
-    if (!attr_set) {
-        CU_CHECK(cudaFuncSetAttribute(col_fmi<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, ColCfg<32>::smem));
-        CU_CHECK(cudaFuncSetAttribute(col_fmi<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ColCfg<16>::smem));
-        attr_set = true;
-    }
-    // Experiment (off by default): pin the 8.5 MB kernel spectrum in L2 with a persisting access-policy window so the ~10 GB of
-    // streaming workspace traffic cannot evict it (ncu: 0.7 GB of DRAM re-reads per launch on c5).  Measured on B200: the
-    // 32 MB set-aside costs more than the re-reads (col_fmi 2.89 -> 3.13 ms), so it stays disabled.
-    static const bool l2_pin = getenv("NDCONV_L2_PIN") != nullptr;
-    if (l2_pin && !p->l2_limit_set) { cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 32u << 20); cudaGetLastError(); p->l2_limit_set = true; }
-    auto launch_col = [&](const ColOptParams &cpar, int grid_cap_mult) {
-        cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
-        attr[0].val.accessPolicyWindow.base_ptr = (void *)cpar.kphys;
-        attr[0].val.accessPolicyWindow.num_bytes = (size_t)F0 * kKphysPitch * sizeof(cf);
-        attr[0].val.accessPolicyWindow.hitRatio = 1.0f;
-        attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-        attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-        cfg.stream = p->stream; cfg.attrs = attr; cfg.numAttrs = l2_pin ? 1 : 0;
-        if (F0 == 1024) {
-            cfg.gridDim = dim3((unsigned)std::min<int64_t>(cpar.nwork, (int64_t)p->num_sms * 2 * grid_cap_mult)); cfg.blockDim = dim3(ColCfg<32>::threads); cfg.dynamicSmemBytes = ColCfg<32>::smem;
-            cudaLaunchKernelEx(&cfg, col_fmi<32>, cpar);
-        } else {
-            cfg.gridDim = dim3((unsigned)std::min<int64_t>(cpar.nwork, (int64_t)p->num_sms * 6 * grid_cap_mult)); cfg.blockDim = dim3(ColCfg<16>::threads); cfg.dynamicSmemBytes = ColCfg<16>::smem;
-            cudaLaunchKernelEx(&cfg, col_fmi<16>, cpar);
-        }
-    };
+    rp.x = (const float *)dev_x; rp.out = (float *)dev_out; rp.ws = (cf *)p->ws.p; rp.tw = tw; rp.twr = twr;
+    rp.rows_per_tile = rows_per_tile; rp.tile_elems = tile_elems;
 
     const double csz = 8.0;
-    double S = (double)(g.P[1] / 2 + 1) * (double)g.P[0], So = (double)(g.P[1] / 2 + 1) * (double)g.O[0];
+    double S = (double)(g.P[al] / 2 + 1), So = S;           // un-inflated half spectrum of the padded array
+    for (int a = 0; a < al; a++) { S *= (double)g.P[a]; So *= (double)g.O[a]; }
     const double in_bytes = 4.0 * (double)g.data_total, out_bytes = 4.0 * (double)g.out_total;
     const stream_t stm = p->stream;
-
-    static const int batch_tiles = getenv("NDCONV_BATCH_TILES") ? atoi(getenv("NDCONV_BATCH_TILES")) : 0;
-    ColOptParams cp; cp.ws = (cf *)p->ws.p; cp.kphys = (const cf *)ent->pair.p; cp.tw = tw_col;
-    if (batch_tiles <= 0) {
-        rp.nwork = pl.ntiles_total * F0;
-        {
-            const int grid = (int)std::min<int64_t>((rp.nwork + 3) / 4, (int64_t)p->num_sms * 4 * 8);
-            st = launch_raw(p->lc(), "row_fwd_pad_r2c", in_bytes + S * csz, [&] { row_fwd_packed<<<grid, 128, 0, stm>>>(rp); }); if (st) return st;
+    auto row_launch = [&](bool inverse) {
+        const int64_t items = (rp.nwork + (32 / T) - 1) / (32 / T);
+        const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((items + 3) / 4, (int64_t)p->num_sms * 4 * 8));
+        switch (T) {
+        case 32: launch_row<32>(inverse, rp, grid, stm); break;
+        case 16: launch_row<16>(inverse, rp, grid, stm); break;
+        case 8: launch_row<8>(inverse, rp, grid, stm); break;
+        default: launch_row<4>(inverse, rp, grid, stm); break;
         }
-        {
-            cp.ntiles_total = pl.ntiles_total; cp.nwork = pl.ntiles_total * (kL / 8);
-            st = launch_raw(p->lc(), "col_fwd_mul_inv", 2 * S * csz + (double)F0 * kKphysPitch * 8, [&] { launch_col(cp, 1); }); if (st) return st;
-        }
-        rp.nwork = g.O[0] * pl.tl[1].ntiles;
-        {
-            const int grid = (int)std::min<int64_t>((rp.nwork + 3) / 4, (int64_t)p->num_sms * 4 * 8);
-            st = launch_raw(p->lc(), "row_inv_c2r_crop", So * csz + out_bytes, [&] { row_inv_packed<<<grid, 128, 0, stm>>>(rp); }); if (st) return st;
-        }
-    } else {
-        // L2-resident schedule: the three kernels run per batch of tiles that share one small workspace
-        const int nt0 = pl.tl[0].ntiles, nt1 = pl.tl[1].ntiles;
-        const double nb = (double)nt0 * ((nt1 + batch_tiles - 1) / batch_tiles);
-        rp.batch = 1;
-        for (int t0 = 0; t0 < nt0; t0++) {
-            const int64_t o_lo = ((int64_t)t0 * pl.tl[0].V + g.s[0] - 1) / g.s[0];
-            const int64_t o_hi = std::min<int64_t>(g.O[0], ((int64_t)(t0 + 1) * pl.tl[0].V + g.s[0] - 1) / g.s[0]);
-            for (int t1b = 0; t1b < nt1; t1b += batch_tiles) {
-                const int nb1 = std::min(batch_tiles, nt1 - t1b);
-                rp.b_t0 = t0; rp.b_t1 = t1b; rp.b_nt1 = nb1; rp.b_o0 = o_lo; rp.b_no0 = std::max<int64_t>(0, o_hi - o_lo);
-                rp.nwork = (int64_t)nb1 * F0;
-                int grid = (int)std::min<int64_t>((rp.nwork + 3) / 4, (int64_t)p->num_sms * 4 * 8);
-                st = launch_raw(p->lc(), "row_fwd_pad_r2c", (in_bytes + S * csz) / nb, [&] { row_fwd_packed<<<grid, 128, 0, stm>>>(rp); }); if (st) return st;
-                cp.ntiles_total = nb1; cp.nwork = (int64_t)nb1 * (kL / 8);
-                st = launch_raw(p->lc(), "col_fwd_mul_inv", (2 * S * csz) / nb, [&] { launch_col(cp, 1); }); if (st) return st;
-                rp.nwork = rp.b_no0 * nb1;
-                if (rp.nwork > 0) {
-                    grid = (int)std::min<int64_t>((rp.nwork + 3) / 4, (int64_t)p->num_sms * 4 * 8);
-                    st = launch_raw(p->lc(), "row_inv_c2r_crop", (So * csz + out_bytes) / nb, [&] { row_inv_packed<<<grid, 128, 0, stm>>>(rp); }); if (st) return st;
-                }
-            }
-        }
-    }
+    };
+    auto col_launch = [&](int axis, int mode, const char *name, double bytes) -> int {
+        fast::ColParams cp; memset(&cp, 0, sizeof(cp));
+        cp.ws = (cf *)p->ws.p; cp.kspec = (const cf *)ent->pair.p; cp.mode = mode;
+        cp.outer = 1; cp.inner = pitch;
+        for (int b = 0; b < axis; b++) cp.outer *= pl.tl[b].F;
+        for (int b = axis + 1; b < al; b++) cp.inner *= pl.tl[b].F;
+        cp.tile_elems = tile_elems; cp.ntiles_total = pl.ntiles_total;
+        cp.nwork = pl.ntiles_total * cp.outer * (cp.inner / 8);
+        const cx<float> *twc = nullptr;
+        int s2 = get_tw_c<float>(p, pl.tl[axis].F, &twc); if (s2) return s2;
+        cp.tw = twc;
+        return launch_raw(p->lc(), name, bytes, [&] { launch_col(pl.tl[axis].F, cp, p->num_sms, stm); });
+    };
+    rp.nwork = pl.ntiles_total * rows_per_tile;
+    st = launch_raw(p->lc(), "row_fwd_pad_r2c", in_bytes + S * csz, [&] { row_launch(false); }); if (st) return st;
+    for (int a = al - 1; a >= 1; a--) { st = col_launch(a, 0, "col_fwd", 2 * S * csz); if (st) return st; }
+    st = col_launch(0, 2, "col_fwd_mul_inv", 2 * S * csz + (double)tile_elems * csz); if (st) return st;
+    for (int a = 1; a <= al - 1; a++) { st = col_launch(a, 1, "col_inv", 2 * S * csz); if (st) return st; }
+    rp.nwork = pl.tl[al].ntiles;
+    for (int a = 0; a < al; a++) rp.nwork *= g.O[a];
+    st = launch_raw(p->lc(), "row_inv_c2r_crop", So * csz + out_bytes, [&] { row_launch(true); }); if (st) return st;
     return NDCONV_OK;
 }
 #endif
@@ -956,7 +990,7 @@ static int conv_fft_t(ndconv_processor *p, const ndconv_problem *pr, PlanEntry *
 #ifdef NDCONV_CUDA
     if (pl.opt2d) {
         if constexpr (sizeof(R) == 4) {
-            st = conv_fft_opt2d(p, pr, g, pl, ml, metabuf, dev_x, dev_out, kent); if (st) return st;
+            st = conv_fft_fast(p, pr, g, pl, ml, metabuf, dev_x, dev_out, kent); if (st) return st;
             if (pr->memory == NDCONV_MEM_HOST) {
                 st = be_d2h(out, dev_out, obytes, p->stream); if (st) return st;
                 st = be_sync(p->stream); if (st) return st;

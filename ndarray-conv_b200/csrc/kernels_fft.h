@@ -18,10 +18,20 @@
 
 namespace ndc {
 
+// exact unsigned division by a run-time constant (n < 2^31): q = (n * mul) >> shift, filled on the host (api.cu)
+struct FastDiv {
+    uint64_t mul;
+    int shift;
+    int d;
+};
+HD int fdiv(int n, const FastDiv &f) { return (int)(((uint64_t)(uint32_t)n * f.mul) >> f.shift); }
+
 template <class R> struct FftPlanDev {
     int L;                       // complex transform length
     int npass;
     int radix[NDC_MAX_PASS];
+    FastDiv by_m[NDC_MAX_PASS];  // butterflies per transform of the pass: L / radix
+    FastDiv by_ns[NDC_MAX_PASS]; // product of the earlier radices
     const cx<R> *tw;             // tw[j] = exp(-2 pi i j / L), j in [0, L)
 };
 
@@ -137,15 +147,21 @@ template <class R, int RDX> HD void dft(cx<R> *v, bool inv)
 // element (b, j) lives at b*bstride + j*estride.  batch_fast: consecutive threads take consecutive b.
 template <class R, int RDX>
 HD void stockham_pass_r(const BlockCtx &c, const cx<R> *in, cx<R> *out, int L, int Ns, const cx<R> *tw, bool inv,
-                        int nbatch, int estride, int bstride, bool batch_fast)
+                        int nbatch, int estride, int bstride, bool batch_fast, const FastDiv &by_m, const FastDiv &by_ns)
 {
     const int m = L / RDX;
     const int total = nbatch * m;
     const int step = L / (Ns * RDX);
+#if defined(__CUDA_ARCH__)
+    const int bshift = 31 - __clz(nbatch > 0 ? nbatch : 1);                           // batch_fast callers pass a power of two
+#else
+    const int bshift = 31 - __builtin_clz((unsigned)(nbatch > 0 ? nbatch : 1));
+#endif
     for (int idx = c.tid; idx < total; idx += c.nt) {
         int b, j;
-        if (batch_fast) { b = idx % nbatch; j = idx / nbatch; } else { j = idx % m; b = idx / m; }
-        const int k = j % Ns;
+        if (batch_fast) { b = idx & (nbatch - 1); j = idx >> bshift; } else { b = fdiv(idx, by_m); j = idx - b * m; }
+        const int jq = fdiv(j, by_ns);
+        const int k = j - jq * Ns;
         cx<R> v[RDX];
         const cx<R> *src = in + (int64_t)b * bstride;
         for (int t = 0; t < RDX; t++) v[t] = src[(int64_t)(j + t * m) * estride];
@@ -157,7 +173,7 @@ HD void stockham_pass_r(const BlockCtx &c, const cx<R> *in, cx<R> *out, int L, i
         }
         dft<R, RDX>(v, inv);
         cx<R> *dst = out + (int64_t)b * bstride;
-        const int j0 = (j / Ns) * Ns * RDX + k;
+        const int j0 = jq * Ns * RDX + k;
         for (int t = 0; t < RDX; t++) dst[(int64_t)(j0 + t * Ns) * estride] = v[t];
     }
 }
@@ -165,21 +181,22 @@ HD void stockham_pass_r(const BlockCtx &c, const cx<R> *in, cx<R> *out, int L, i
 // Full transform: data starts in `a`, ping-pongs with `b`; returns the buffer holding the result.
 template <class R>
 HD cx<R> *fft_smem(const BlockCtx &c, cx<R> *a, cx<R> *b, const FftPlanDev<R> &pl, bool inv,
-                   int nbatch, int estride, int bstride, bool batch_fast)
+                   int nbatch, int estride, int bstride, bool batch_fast, const cx<R> *tw_override = nullptr)
 {
+    const cx<R> *tw = tw_override ? tw_override : pl.tw;       // shared-memory copy of the twiddle table when the kernel made one
     int Ns = 1;
     cx<R> *in = a, *out = b;
     for (int p = 0; p < pl.npass; p++) {
         const int r = pl.radix[p];
         switch (r) {
-        case 2: stockham_pass_r<R, 2>(c, in, out, pl.L, Ns, pl.tw, inv, nbatch, estride, bstride, batch_fast); break;
-        case 3: stockham_pass_r<R, 3>(c, in, out, pl.L, Ns, pl.tw, inv, nbatch, estride, bstride, batch_fast); break;
-        case 4: stockham_pass_r<R, 4>(c, in, out, pl.L, Ns, pl.tw, inv, nbatch, estride, bstride, batch_fast); break;
-        case 5: stockham_pass_r<R, 5>(c, in, out, pl.L, Ns, pl.tw, inv, nbatch, estride, bstride, batch_fast); break;
-        case 7: stockham_pass_r<R, 7>(c, in, out, pl.L, Ns, pl.tw, inv, nbatch, estride, bstride, batch_fast); break;
-        case 16: stockham_pass_r<R, 16>(c, in, out, pl.L, Ns, pl.tw, inv, nbatch, estride, bstride, batch_fast); break;
-        case 32: stockham_pass_r<R, 32>(c, in, out, pl.L, Ns, pl.tw, inv, nbatch, estride, bstride, batch_fast); break;
-        default: stockham_pass_r<R, 8>(c, in, out, pl.L, Ns, pl.tw, inv, nbatch, estride, bstride, batch_fast); break;
+        case 2: stockham_pass_r<R, 2>(c, in, out, pl.L, Ns, tw, inv, nbatch, estride, bstride, batch_fast, pl.by_m[p], pl.by_ns[p]); break;
+        case 3: stockham_pass_r<R, 3>(c, in, out, pl.L, Ns, tw, inv, nbatch, estride, bstride, batch_fast, pl.by_m[p], pl.by_ns[p]); break;
+        case 4: stockham_pass_r<R, 4>(c, in, out, pl.L, Ns, tw, inv, nbatch, estride, bstride, batch_fast, pl.by_m[p], pl.by_ns[p]); break;
+        case 5: stockham_pass_r<R, 5>(c, in, out, pl.L, Ns, tw, inv, nbatch, estride, bstride, batch_fast, pl.by_m[p], pl.by_ns[p]); break;
+        case 7: stockham_pass_r<R, 7>(c, in, out, pl.L, Ns, tw, inv, nbatch, estride, bstride, batch_fast, pl.by_m[p], pl.by_ns[p]); break;
+        case 16: stockham_pass_r<R, 16>(c, in, out, pl.L, Ns, tw, inv, nbatch, estride, bstride, batch_fast, pl.by_m[p], pl.by_ns[p]); break;
+        case 32: stockham_pass_r<R, 32>(c, in, out, pl.L, Ns, tw, inv, nbatch, estride, bstride, batch_fast, pl.by_m[p], pl.by_ns[p]); break;
+        default: stockham_pass_r<R, 8>(c, in, out, pl.L, Ns, tw, inv, nbatch, estride, bstride, batch_fast, pl.by_m[p], pl.by_ns[p]); break;
         }
         Ns *= r;
         c.sync();
@@ -208,6 +225,7 @@ template <class R> struct RowParams {
     int64_t tile_elems;         // rows_per_tile * Hp
     int64_t nwork;
     R scale;                    // applied by the final store; 0 = none (conv_fft folds 1/len into the kernel spectrum)
+    int tw_smem_off;            // > 0: byte offset of a shared-memory copy of the twiddle table (loaded once per CTA)
 };
 
 template <class R> struct ColParams {
@@ -217,7 +235,18 @@ template <class R> struct ColParams {
     int64_t inner, outer, tile_elems, ntiles_total;
     FftPlanDev<R> plan;
     int64_t nwork;              // ntiles_total * outer * (inner / W)
+    int tw_smem_off;            // > 0: byte offset of a shared-memory copy of the twiddle table
 };
+
+// copy the twiddle table into shared memory once per CTA (saves one dependent global load per butterfly input)
+template <class R> HD const cx<R> *stage_twiddles(const BlockCtx &c, const FftPlanDev<R> &pl, int off)
+{
+    if (off <= 0) return nullptr;
+    cx<R> *s = (cx<R> *)(c.smem + off);
+    for (int i = c.tid; i < pl.L; i += c.nt) s[i] = pl.tw[i];
+    c.sync();
+    return s;
+}
 
 // ---- row helpers -----------------------------------------------------------------------------------
 // Resolution of the axes below the last one for one row of one tile (see padded_at in kernels_direct.h).
@@ -309,6 +338,7 @@ template <class R> struct RowFwdBody {
         const int F = p.F[N - 1];
         cx<R> *bufA = (cx<R> *)c.smem, *bufB = bufA + (size_t)B * zs;
         RowSrc<R> *rsrc = (RowSrc<R> *)(bufB + (size_t)B * zs);
+        const cx<R> *stw = stage_twiddles(c, p.plan, p.tw_smem_off);
         const int64_t groups_per_tile = (p.rows_per_tile + B - 1) / B;
         for (int64_t w = c.bid; w < p.nwork; w += c.nb) {
             const int64_t tile = w / groups_per_tile, row0 = (w % groups_per_tile) * B;
@@ -333,7 +363,7 @@ template <class R> struct RowFwdBody {
                 else ((R *)(bufA + (size_t)b * zs))[i] = gather_elem<R, R>(p, rs, cl0 + i, (R)0);
             }
             c.sync();
-            cx<R> *res = fft_smem(c, bufA, bufB, p.plan, false, nrows, 1, zs, false);
+            cx<R> *res = fft_smem(c, bufA, bufB, p.plan, false, nrows, 1, zs, false, stw);
             cx<R> *dst = p.ws + tile * p.tile_elems + row0 * p.Hp;
             if (p.is_cx) {
                 for (int idx = c.tid; idx < nrows * p.Hp; idx += c.nt) {
@@ -381,6 +411,7 @@ template <class R> struct RowInvBody {
         const int N = p.ndim, L = p.plan.L, B = p.B, zs = L + 1;
         cx<R> *bufA = (cx<R> *)c.smem, *bufB = bufA + (size_t)B * zs;
         int64_t *orow_base = (int64_t *)(bufB + (size_t)B * zs);
+        const cx<R> *stw = stage_twiddles(c, p.plan, p.tw_smem_off);
         int64_t out_rows = 1;
         for (int a = 0; a < N - 1; a++) out_rows *= p.O[a];
         const int64_t groups = (out_rows + B - 1) / B;
@@ -411,11 +442,11 @@ template <class R> struct RowInvBody {
             }
             c.sync();
             cx<R> *res;
-            if (p.is_cx) res = fft_smem(c, bufA, bufB, p.plan, true, nrows, 1, zs, false);
+            if (p.is_cx) res = fft_smem(c, bufA, bufB, p.plan, true, nrows, 1, zs, false, stw);
             else {
                 c2r_pre(c, bufA, bufB, L, p.twr, nrows, zs, zs);
                 c.sync();
-                res = fft_smem(c, bufB, bufA, p.plan, true, nrows, 1, zs, false);
+                res = fft_smem(c, bufB, bufA, p.plan, true, nrows, 1, zs, false, stw);
             }
             crop_store_row(c, p, res, zs, nrows, orow_base, tl);
             c.sync();
@@ -430,6 +461,7 @@ template <class R> struct Row1DBody {
         const int L = p.plan.L, zs = L + 1, F = p.F[0];
         cx<R> *bufA = (cx<R> *)c.smem, *bufB = bufA + zs;
         int64_t *orow_base = (int64_t *)(bufB + zs);
+        const cx<R> *stw = stage_twiddles(c, p.plan, p.tw_smem_off);
         for (int64_t w = c.bid; w < p.nwork; w += c.nb) {
             const int64_t cl0 = w * p.V[0];
             RowSrc<R> rs; rs.zero = false; rs.beyond = false; rs.has_const = false; rs.cval = nullptr; rs.base = 0;
@@ -439,12 +471,12 @@ template <class R> struct Row1DBody {
             }
             if (c.tid == 0) orow_base[0] = 0;
             c.sync();
-            cx<R> *res = fft_smem(c, bufA, bufB, p.plan, false, 1, 1, zs, false);
+            cx<R> *res = fft_smem(c, bufA, bufB, p.plan, false, 1, 1, zs, false, stw);
             cx<R> *oth = (res == bufA) ? bufB : bufA;
             if (p.is_cx) {
                 for (int k = c.tid; k < L; k += c.nt) res[k] = cmul(res[k], p.kspec[k]);
                 c.sync();
-                res = fft_smem(c, res, oth, p.plan, true, 1, 1, zs, false);
+                res = fft_smem(c, res, oth, p.plan, true, 1, 1, zs, false, stw);
             } else {
                 r2c_post(c, res, oth, L, p.twr, 1, zs, zs);
                 c.sync();
@@ -452,7 +484,7 @@ template <class R> struct Row1DBody {
                 c.sync();
                 c2r_pre(c, oth, res, L, p.twr, 1, zs, zs);
                 c.sync();
-                res = fft_smem(c, res, oth, p.plan, true, 1, 1, zs, false);
+                res = fft_smem(c, res, oth, p.plan, true, 1, 1, zs, false, stw);
             }
             crop_store_row(c, p, res, zs, 1, orow_base, w);
             c.sync();
@@ -467,6 +499,7 @@ template <class R> struct ColBody {
     {
         const int F = p.F, W = p.W;
         cx<R> *bufA = (cx<R> *)c.smem, *bufB = bufA + (size_t)F * W;
+        const cx<R> *stw = stage_twiddles(c, p.plan, p.tw_smem_off);
         const int64_t iblocks = p.inner / W;
         for (int64_t w = c.bid; w < p.nwork; w += c.nb) {
             const int64_t ib = w % iblocks, o = (w / iblocks) % p.outer, tile = w / (iblocks * p.outer);
@@ -474,12 +507,12 @@ template <class R> struct ColBody {
             cx<R> *g = p.ws + tile * p.tile_elems + rel;
             for (int idx = c.tid; idx < F * W; idx += c.nt) bufA[idx] = g[(int64_t)(idx / W) * p.inner + idx % W];
             c.sync();
-            cx<R> *res = fft_smem(c, bufA, bufB, p.plan, p.mode == 1, W, W, 1, true);
+            cx<R> *res = fft_smem(c, bufA, bufB, p.plan, p.mode == 1, W, W, 1, true, stw);
             if (p.mode == 2) {
                 const cx<R> *ks = p.kspec + rel;
                 for (int idx = c.tid; idx < F * W; idx += c.nt) res[idx] = cmul(res[idx], ks[(int64_t)(idx / W) * p.inner + idx % W]);
                 c.sync();
-                res = fft_smem(c, res, res == bufA ? bufB : bufA, p.plan, true, W, W, 1, true);
+                res = fft_smem(c, res, res == bufA ? bufB : bufA, p.plan, true, W, W, 1, true, stw);
             }
             for (int idx = c.tid; idx < F * W; idx += c.nt) g[(int64_t)(idx / W) * p.inner + idx % W] = res[idx];
             c.sync();

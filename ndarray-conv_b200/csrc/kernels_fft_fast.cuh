@@ -1,0 +1,524 @@
+// kernels_fft_fast.cuh -- sm_100a fast path of the real f32 conv_fft pipeline, rank 2 and 3 (device only).
+//
+// Overlap-save tiles of F0 [x F1] x F_last real samples.  The last axis is a half-length real transform: F_last = 2L reals
+// are packed as L = 32*T complex (T = 4, 8, 16, 32 lanes per row, 32 complex per lane).  Other axes: F = E*Tc, E = 8, 16, 32
+// rows per thread, Tc = E, E/2 or E/4 threads per column (F = 16 .. 1024).
+//
+// Workspace layout per tile: rows of PITCH = L + 8 complex.  Columns [0, L) hold the half spectrum in PAIRED order -- slot k
+// in [1, L/2) = (X[k], X[L-k]), slot 0 = (X[0], X[L/2]) -- so a row kernel emits 16-byte stores and the partner bins needed by
+// the real-transform algebra are adjacent; column L holds the Nyquist bin X[L]; columns L+1 .. L+7 are zero.  Every column is an
+// ordinary complex column for the other axes, which is what lets the same kernels serve rank 3.
+//
+//   row_fwd<T>      one lane-group of T lanes per row (32/T rows per warp, no block barrier): border-mapped or plain vector
+//                   loads into registers, radix-32 over the register index, twiddle, warp-private shared-memory exchange,
+//                   radix-T; Z[L-k] comes from its owner lane by __shfl_sync; R2C post-processing X[k] = E + w^k O in registers.
+//   col_pass<E,Tc>  Tc*8 threads per F x 8-column tile (64-byte row segments): radix-E, twiddle, padded exchange, radix-Tc;
+//                   mode FWD / INV / FMI (forward, multiply by the cached kernel spectrum, inverse -- in place).  The next tile is
+//                   staged into the idle exchange buffer with 16-byte cp.async while the last pass and the stores run.
+//   row_inv<T>      one lane-group per (output row, last-axis tile): cp.async-prefetched paired loads, C2R pre-processing in
+//                   registers, shuffle, inverse radix-T, exchange, inverse radix-32, crop [Kd-1, F) and stride fused into the store.
+//
+// Reference stages replaced: conv_fft/padding.rs:30-62, processor/real.rs:105-154, mod.rs:268, real.rs:233-280, mod.rs:282-289.
+#pragma once
+#include "kernels_fft.h"
+
+#ifdef NDCONV_CUDA
+namespace ndc {
+namespace fast {
+
+typedef cx<float> cf;
+constexpr int kPad = 8;          // extra columns per row: Nyquist + 7 zeros (keeps rows 64-byte aligned; 128-byte rows measured no faster)
+
+__device__ __forceinline__ cf ld_cf(const cf *p) { float2 t = *reinterpret_cast<const float2 *>(p); return cf{t.x, t.y}; }
+__device__ __forceinline__ void st_cf(cf *p, cf v) { *reinterpret_cast<float2 *>(p) = make_float2(v.re, v.im); }
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+struct RowParams {
+    int ndim;                                  // 2 or 3
+    int64_t n[3], xstr[3], P[3], pf[3];
+    const int32_t *map[3];
+    float cfront[3], cback[3];
+    int F[3], V[3], ntiles[3], Kd[3];          // F[ndim-1] = 2L
+    int64_t s[3], O[3];
+    const float *x;
+    float *out;
+    cf *ws;
+    const cf *tw;                              // exp(-2 pi i j / L), j < L
+    const cf *twr;                             // exp(-2 pi i k / 2L), k <= L/2
+    int64_t nwork;                             // rows to transform (fwd) / (output row, tile) pairs (inv)
+    int64_t rows_per_tile, tile_elems;         // prod of the outer F ; rows_per_tile * (L + 8)
+};
+
+// ---- row forward ---------------------------------------------------------------------------------------------------------
+template <int T> struct RowCfg {
+    static constexpr int L = 32 * T, M = 32 / T, G = 32 / T;          // complex length, radix-T butterflies per lane, rows per warp
+    static constexpr int gstride = 32 * (T + 1) + T;                  // exchange buffer of one lane-group (complex elements)
+    static constexpr int wstride = (G * gstride > (L + 2) * G ? G * gstride : (L + 2) * G);   // staging: L/2 + 1 float4 per group
+    static constexpr int smem = (L + L / 2 + 4 * wstride) * 8;        // W_L table, w^k table, 4 warps of exchange buffers
+};
+
+struct RowSrcInfo {
+    int64_t base, cl0;
+    float cval;
+    bool zero, has_const, beyond, active;
+    cf *dst;
+};
+
+// outer-axis resolution of one tile row: beyond the padded extent of an outer axis the FFT buffer is zero
+// (conv_fft/padding.rs:47-59); otherwise the highest-numbered constant axis wins and never-written cells read 0
+template <int N> __device__ __forceinline__ RowSrcInfo resolve_fwd_row(const RowParams &p, int64_t w, int L)
+{
+    RowSrcInfo r; r.base = 0; r.cval = 0.f; r.zero = false; r.has_const = false; r.beyond = false; r.active = w < p.nwork; r.dst = nullptr; r.cl0 = 0;
+    if (!r.active) return r;
+    // 32-bit index arithmetic (the host only takes this path when the work count fits; 64-bit division is ~5x dearer)
+    const uint32_t w32 = (uint32_t)w, rpt = (uint32_t)p.rows_per_tile;
+    const uint32_t tile = w32 / rpt;
+    uint32_t row = w32 - tile * rpt;
+    r.dst = p.ws + (int64_t)tile * p.tile_elems + (int64_t)row * (L + kPad);
+    uint32_t tt = tile;
+    const uint32_t tl = tt % (uint32_t)p.ntiles[N - 1]; tt /= (uint32_t)p.ntiles[N - 1];
+    r.cl0 = (int64_t)tl * p.V[N - 1];
+    int64_t c[2] = {0, 0};
+#pragma unroll
+    for (int a = N - 2; a >= 0; a--) {
+        const uint32_t ta = tt % (uint32_t)p.ntiles[a]; tt /= (uint32_t)p.ntiles[a];
+        const uint32_t ra = row % (uint32_t)p.F[a]; row /= (uint32_t)p.F[a];
+        c[a] = (int64_t)ta * p.V[a] + ra;
+        if (c[a] >= p.P[a]) r.beyond = true;
+    }
+    if (r.beyond) return r;
+#pragma unroll
+    for (int a = N - 2; a >= 0; a--) {
+        if (r.has_const) continue;
+        const int32_t m = p.map[a][c[a]];
+        if (m >= 0) r.base += (int64_t)m * p.xstr[a];
+        else if (m == NDC_MAP_INIT) r.zero = true;
+        else { r.has_const = true; r.cval = (m == NDC_MAP_CONST_FRONT) ? p.cfront[a] : p.cback[a]; }
+    }
+    return r;
+}
+
+template <int T, int N>
+__global__ void __launch_bounds__(128, 4) row_fwd(const __grid_constant__ RowParams p)
+{
+    constexpr int L = RowCfg<T>::L, M = RowCfg<T>::M, G = RowCfg<T>::G;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cf *s_tw = reinterpret_cast<cf *>(smem_raw);          // s_tw[k1 * T + t] = W_L^{t k1}
+    cf *s_twr = s_tw + L;                                 // w^k, k < L/2
+    cf *s_ex = s_twr + L / 2;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane / T, t = lane % T;
+    for (int idx = threadIdx.x; idx < L; idx += blockDim.x) s_tw[idx] = p.tw[(idx / T) * (idx % T)];
+    for (int idx = threadIdx.x; idx < L / 2; idx += blockDim.x) s_twr[idx] = p.twr[idx];
+    __syncthreads();
+    cf *sb = s_ex + warp * RowCfg<T>::wstride + g * RowCfg<T>::gstride;
+    constexpr int al = N - 1;
+    const int src_lane = g * T + ((T - t) % T);
+    const int64_t nwarp_items = (p.nwork + G - 1) / G;
+    for (int64_t wi = (int64_t)blockIdx.x * 4 + warp; wi < nwarp_items; wi += (int64_t)gridDim.x * 4) {
+        const RowSrcInfo ri = resolve_fwd_row<N>(p, wi * G + g, L);
+        if (__all_sync(0xffffffffu, !ri.active || ri.beyond)) {
+            // rows beyond the padded extent of an outer axis: zero spectrum, no transform
+            if (ri.active) {
+                float4 *z4 = reinterpret_cast<float4 *>(ri.dst);
+                for (int q = t; q < (L + kPad) / 2; q += T) z4[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            continue;
+        }
+        cf v[32];
+        // a beyond-extent / zero row without a constant last axis is all zero -- but the last axis may still be a constant border
+        const bool interior = ri.active && !ri.beyond && !ri.zero && !ri.has_const && p.xstr[al] == 1 && ri.cl0 >= p.pf[al] && ri.cl0 + 2 * L <= p.pf[al] + p.n[al];
+        if (interior) {
+            const float *src = p.x + ri.base + (ri.cl0 - p.pf[al]);
+            if ((reinterpret_cast<uintptr_t>(src) & 7) == 0) {
+                const float2 *s2 = reinterpret_cast<const float2 *>(src);
+#pragma unroll
+                for (int j = 0; j < 32; j++) { const float2 q = __ldg(s2 + t + T * j); v[j] = cf{q.x, q.y}; }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; j++) { const int e = 2 * (t + T * j); v[j] = cf{__ldg(src + e), __ldg(src + e + 1)}; }
+            }
+        } else {
+            const bool beyond = ri.beyond;
+            const bool plain = ri.active && !beyond && !ri.zero && !ri.has_const;
+#pragma unroll
+            for (int j = 0; j < 32; j++) {
+                float q[2];
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const int64_t cl = ri.cl0 + 2 * (t + T * j) + h;
+                    float val = 0.f;
+                    const int64_t cc = cl - p.pf[al];
+                    if (plain && cc >= 0 && cc < p.n[al]) val = __ldg(p.x + ri.base + cc * p.xstr[al]);      // in-array sample: no map lookup
+                    else if (ri.active && !beyond && cl < p.P[al]) {
+                        const int32_t m = p.map[al][cl];
+                        if (m == NDC_MAP_CONST_FRONT) val = p.cfront[al];
+                        else if (m == NDC_MAP_CONST_BACK) val = p.cback[al];
+                        else if (ri.has_const) val = ri.cval;
+                        else if (m != NDC_MAP_INIT && !ri.zero) val = __ldg(p.x + ri.base + (int64_t)m * p.xstr[al]);
+                    }
+                    q[h] = val;
+                }
+                v[j] = cf{q[0], q[1]};
+            }
+        }
+        dft32<float>(v, false);                                          // over j -> k1
+#pragma unroll
+        for (int k1 = 0; k1 < 32; k1++) sb[k1 * (T + 1) + t] = cmul(v[k1], s_tw[k1 * T + t]);
+        __syncwarp();
+#pragma unroll
+        for (int m = 0; m < M; m++)
+#pragma unroll
+            for (int i = 0; i < T; i++) v[m * T + i] = sb[(t + T * m) * (T + 1) + i];
+        __syncwarp();
+#pragma unroll
+        for (int m = 0; m < M; m++) dft<float, T>(v + m * T, false);      // v[m*T + k2] = Z[k], k = t + T m + 32 k2
+        // partner Z[L-k] and R2C post-processing; primaries are k2 < T/2 (k < L/2)
+        float4 *dst4 = reinterpret_cast<float4 *>(ri.dst);
+#pragma unroll
+        for (int m = 0; m < M; m++) {
+#pragma unroll
+            for (int k2 = 0; k2 < T / 2; k2++) {
+                const int ia = (M - 1 - m) * T + (T - 1 - k2);                                    // lanes t > 0
+                const int ib = ((M - m) % M) * T + (m > 0 ? T - 1 - k2 : (k2 > 0 ? T - k2 : T / 2)); // lane t == 0 (own registers)
+                float px = __shfl_sync(0xffffffffu, v[ia].re, src_lane);
+                float py = __shfl_sync(0xffffffffu, v[ia].im, src_lane);
+                if (t == 0) { px = v[ib].re; py = v[ib].im; }
+                const cf zk = v[m * T + k2];
+                const int k = t + T * m + 32 * k2;
+                float4 o4;
+                if (k == 0) {
+                    o4 = make_float4(zk.re + zk.im, 0.f, px, -py);                                 // X[0] ; X[L/2] = conj Z[L/2]
+                    if (ri.active) *reinterpret_cast<float4 *>(ri.dst + L) = make_float4(zk.re - zk.im, 0.f, 0.f, 0.f);   // Nyquist X[L]
+                } else {
+                    const cf E = cf{0.5f * (zk.re + px), 0.5f * (zk.im - py)};
+                    const cf O = cf{0.5f * (zk.im + py), -0.5f * (zk.re - px)};
+                    const cf tw = cmul(s_twr[k], O);
+                    o4 = make_float4(E.re + tw.re, E.im + tw.im, E.re - tw.re, -(E.im - tw.im));
+                }
+                if (ri.active) dst4[k] = o4;
+            }
+        }
+        if (ri.active && t > 0 && t < 4) *reinterpret_cast<float4 *>(ri.dst + L + 2 * t) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
+// ---- row inverse + crop + decimate -------------------------------------------------------------------------------------------
+struct RowInvInfo {
+    const cf *src;
+    int64_t orow;      // output element offset of the row
+    int tl;
+    bool active;
+};
+template <int N> __device__ __forceinline__ RowInvInfo resolve_inv_row(const RowParams &p, int64_t w, int L)
+{
+    RowInvInfo r; r.active = w < p.nwork; r.src = p.ws; r.orow = 0; r.tl = 0;
+    if (!r.active) return r;
+    const uint32_t ntl = (uint32_t)p.ntiles[N - 1];
+    const uint32_t w32 = (uint32_t)w;
+    r.tl = (int)(w32 % ntl);
+    uint32_t orow = w32 / ntl;                   // row-major index over the outer output axes (fits 32 bits, checked on the host)
+    uint32_t o[2] = {0, 0};
+#pragma unroll
+    for (int a = N - 2; a >= 0; a--) { o[a] = orow % (uint32_t)p.O[a]; orow /= (uint32_t)p.O[a]; }
+    int64_t tile = 0, row = 0, obase = 0;
+#pragma unroll
+    for (int a = 0; a < N - 1; a++) {
+        const uint32_t q = o[a] * (uint32_t)p.s[a];
+        const uint32_t ta = q / (uint32_t)p.V[a];
+        const uint32_t ra = q - ta * (uint32_t)p.V[a] + (uint32_t)p.Kd[a] - 1;
+        tile = tile * p.ntiles[a] + ta;
+        row = row * p.F[a] + ra;
+        obase = obase * p.O[a] + o[a];
+    }
+    tile = tile * ntl + r.tl;
+    r.src = p.ws + tile * p.tile_elems + row * (L + kPad);
+    r.orow = obase * p.O[N - 1];
+    return r;
+}
+
+template <int T, int N>
+__global__ void __launch_bounds__(128, 4) row_inv(const __grid_constant__ RowParams p)
+{
+    constexpr int L = RowCfg<T>::L, M = RowCfg<T>::M, G = RowCfg<T>::G;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cf *s_tw = reinterpret_cast<cf *>(smem_raw);          // TRANSPOSED for the inverse flow: s_tw[i * 32 + k1] = W_L^{i k1} (k1 is the lane-dependent index)
+    cf *s_twr = s_tw + L;
+    cf *s_ex = s_twr + L / 2;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane / T, t = lane % T;
+    for (int idx = threadIdx.x; idx < L; idx += blockDim.x) s_tw[idx] = p.tw[(idx >> 5) * (idx & 31)];
+    for (int idx = threadIdx.x; idx < L / 2; idx += blockDim.x) s_twr[idx] = p.twr[idx];
+    __syncthreads();
+    cf *sb = s_ex + warp * RowCfg<T>::wstride + g * RowCfg<T>::gstride;
+    float4 *sb4 = reinterpret_cast<float4 *>(s_ex + warp * RowCfg<T>::wstride) + g * (L / 2 + 1);  // staging: L/2 slots + the Nyquist column, linear
+    constexpr int al = N - 1;
+    const int src_lane = g * T + ((T - t) % T);
+    const int64_t nwarp_items = (p.nwork + G - 1) / G;
+    const int64_t wstep = (int64_t)gridDim.x * 4;
+    int64_t wi = (int64_t)blockIdx.x * 4 + warp;
+    if (wi >= nwarp_items) return;
+    RowInvInfo ri = resolve_inv_row<N>(p, wi * G + g, L);
+    auto stage = [&](const RowInvInfo &r) {
+        if (r.active) {
+            const float4 *s4 = reinterpret_cast<const float4 *>(r.src);
+#pragma unroll
+            for (int q = 0; q < 16; q++) cp_async16(sb4 + t + T * q, s4 + t + T * q);
+            if (t == 0) cp_async16(sb4 + L / 2, s4 + L / 2);             // column L: the Nyquist bin
+        }
+        cp_async_commit();
+    };
+    stage(ri);
+    for (; wi < nwarp_items; wi += wstep) {
+        cf v[32], b[16];
+        cp_async_wait_all();
+        __syncwarp();
+        const float nyq = sb4[L / 2].x;
+        // C2R pre-processing (x2): Z[k] = E + i O, Z[L-k] = conj(E) + i conj(O), E = Y[k] + conj Y[L-k], O = conj(w^k)(Y[k] - conj Y[L-k])
+#pragma unroll
+        for (int m = 0; m < M; m++) {
+#pragma unroll
+            for (int k2 = 0; k2 < T / 2; k2++) {
+                const int k = t + T * m + 32 * k2;
+                const float4 q = sb4[k];
+                cf zk, zp;
+                if (k == 0) {
+                    zk = cf{q.x + nyq, q.x - nyq};                              // Z[0] from the real DC / Nyquist bins
+                    zp = cf{2.f * q.z, -2.f * q.w};                             // Z[L/2] = 2 conj Y[L/2]
+                } else {
+                    const cf E = cf{q.x + q.z, q.y - q.w};
+                    const cf D = cf{q.x - q.z, q.y + q.w};
+                    const cf O = cmulc(D, s_twr[k]);
+                    zk = cf{E.re - O.im, E.im + O.re};
+                    zp = cf{E.re + O.im, -E.im + O.re};
+                }
+                v[m * T + k2] = zk;
+                b[m * (T / 2) + k2] = zp;
+            }
+        }
+        __syncwarp();
+        // deliver Z[L-k] to its owner: register (mr, k2r >= T/2) of lane t comes from lane (T-t)%T
+#pragma unroll
+        for (int mr = 0; mr < M; mr++) {
+#pragma unroll
+            for (int k2r = T / 2; k2r < T; k2r++) {
+                const int ia = (M - 1 - mr) * (T / 2) + (T - 1 - k2r);                                            // source lanes t' > 0
+                const int ib = mr > 0 ? (M - mr) * (T / 2) + (T - 1 - k2r) : (k2r == T / 2 ? 0 : (T - k2r));      // lane 0: own b[]
+                float px = __shfl_sync(0xffffffffu, b[ia].re, src_lane);
+                float py = __shfl_sync(0xffffffffu, b[ia].im, src_lane);
+                if (t == 0) { px = b[ib].re; py = b[ib].im; }
+                v[mr * T + k2r] = cf{px, py};
+            }
+        }
+        // inverse: radix T over k2, conj twiddle, exchange, radix 32 over k1
+#pragma unroll
+        for (int m = 0; m < M; m++) dft<float, T>(v + m * T, true);
+#pragma unroll
+        for (int m = 0; m < M; m++)
+#pragma unroll
+            for (int i = 0; i < T; i++) sb[(t + T * m) * (T + 1) + i] = cmulc(v[m * T + i], s_tw[i * 32 + (t + T * m)]);
+        __syncwarp();
+#pragma unroll
+        for (int k1 = 0; k1 < 32; k1++) v[k1] = sb[k1 * (T + 1) + t];
+        __syncwarp();
+        const RowInvInfo cur = ri;
+        if (wi + wstep < nwarp_items) { ri = resolve_inv_row<N>(p, (wi + wstep) * G + g, L); stage(ri); }
+        dft32<float>(v, true);                                           // v[j] = z[t + T j] = (y[2n], y[2n+1]), n = t + T j
+        if (!cur.active) continue;
+        const int Kd1 = p.Kd[al];
+        const int64_t mbase = (int64_t)cur.tl * p.V[al];
+        if (p.s[al] == 1) {
+            const int64_t obase = cur.orow + mbase - (Kd1 - 1);
+            const bool vec_ok = (obase & 1) == 0;
+#pragma unroll
+            for (int j = 0; j < 32; j++) {
+                const int i = 2 * (t + T * j);
+                const int64_t o_lo = mbase + i - (Kd1 - 1);
+                const bool ok0 = i >= Kd1 - 1 && o_lo < p.O[al];
+                const bool ok1 = i + 1 >= Kd1 - 1 && o_lo + 1 < p.O[al];
+                if (vec_ok && ok0 && ok1) *reinterpret_cast<float2 *>(p.out + cur.orow + o_lo) = make_float2(v[j].re, v[j].im);
+                else {
+                    if (ok0) p.out[cur.orow + o_lo] = v[j].re;
+                    if (ok1) p.out[cur.orow + o_lo + 1] = v[j].im;
+                }
+            }
+        } else {
+            const int64_t s1 = p.s[al];
+#pragma unroll
+            for (int j = 0; j < 32; j++) {
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const int i = 2 * (t + T * j) + h;
+                    if (i < Kd1 - 1) continue;
+                    const int64_t q = mbase + i - (Kd1 - 1);
+                    if (q % s1) continue;
+                    const int64_t o = q / s1;
+                    if (o < p.O[al]) p.out[cur.orow + o] = h ? v[j].im : v[j].re;
+                }
+            }
+        }
+    }
+}
+
+// ---- column pass: FWD / INV / FMI ---------------------------------------------------------------------------------------------
+struct ColParams {
+    cf *ws;
+    const cf *kspec;        // kernel spectrum, same (outer, F, inner) geometry as one tile (FMI only)
+    const cf *tw;           // exp(-2 pi i j / F)
+    int mode;               // 0 forward, 1 inverse, 2 forward * kspec * inverse
+    int64_t outer, inner;   // the tile is [outer][F][inner] complex, inner % 8 == 0
+    int64_t tile_elems, ntiles_total;
+    int64_t nwork;          // ntiles_total * outer * inner / 8
+};
+
+template <int E, int Tc> struct ColCfg {
+    static constexpr int F = E * Tc, Mc = E / Tc;
+    static constexpr int threads = Tc * 8;
+    static constexpr int pitch = Tc * 8 + 8;                             // padded k1-row stride of the exchange buffer
+    static constexpr int ex = (E * pitch > F * 8 ? E * pitch : F * 8);
+    static constexpr int smem = ((Tc == E ? 1 : 2) * F + ex) * 8;         // forward table, transposed table for the inverse when Tc != E, exchange buffer
+    static constexpr int min_blocks = E == 32 ? (Tc == 32 ? 2 : 3) : 4;
+};
+
+template <int E, int Tc>
+__global__ void __launch_bounds__(ColCfg<E, Tc>::threads, ColCfg<E, Tc>::min_blocks) col_pass(const __grid_constant__ ColParams p)
+{
+    using C = ColCfg<E, Tc>;
+    constexpr int F = C::F, Mc = C::Mc, pitch = C::pitch;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cf *s_tw = reinterpret_cast<cf *>(smem_raw);        // s_tw[k1 * Tc + i] = W_F^{i k1}, k1 < E, i < Tc   (forward: i is the thread index)
+    cf *s_twT = s_tw + F;                               // s_twT[ii * E + k1] = W_F^{ii k1}   (inverse, Tc != E: k1 is the thread-dependent index)
+    cf *S = s_tw + (Tc == E ? 1 : 2) * F;
+    const int tid = threadIdx.x;
+    const int c = tid & 7, i = tid >> 3;                // column of the block, thread index inside the column (< Tc)
+    for (int idx = tid; idx < F; idx += C::threads) { s_tw[idx] = p.tw[(idx / Tc) * (idx % Tc)]; if (Tc != E) s_twT[idx] = p.tw[(idx / E) * (idx % E)]; }
+    const int64_t iblocks = p.inner / 8;
+    auto tile_ptr = [&](int64_t w) {
+        const int64_t ib = w % iblocks, o = (w / iblocks) % p.outer, tile = w / (iblocks * p.outer);
+        return p.ws + tile * p.tile_elems + o * (int64_t)F * p.inner + ib * 8;
+    };
+    constexpr int kChunks = (F * 4 + C::threads - 1) / C::threads;       // 16-byte chunks per thread
+    auto prefetch = [&](int64_t wn) {
+        const cf *gn = tile_ptr(wn);
+#pragma unroll
+        for (int m = 0; m < kChunks; m++) {
+            const int id = tid + C::threads * m, row = id >> 2, part = id & 3;
+            if (F * 4 % C::threads == 0 || id < F * 4) cp_async16(S + row * 8 + part * 2, gn + (int64_t)row * p.inner + part * 2);
+        }
+        cp_async_commit();
+    };
+    if ((int64_t)blockIdx.x < p.nwork) prefetch(blockIdx.x);
+    for (int64_t w = blockIdx.x; w < p.nwork; w += gridDim.x) {
+        cf *gt = tile_ptr(w) + c;
+        cf v[E];
+        cp_async_wait_all();
+        __syncthreads();
+        if (p.mode != 1) {
+            // ---- forward: rows i + Tc j -> radix E -> twiddle -> exchange -> radix Tc -> rows q = (i + Tc m) + E k2 ----
+#pragma unroll
+            for (int j = 0; j < E; j++) v[j] = S[(i + Tc * j) * 8 + c];
+            __syncthreads();
+            dft<float, E>(v, false);
+#pragma unroll
+            for (int k1 = 0; k1 < E; k1++) S[k1 * pitch + i * 8 + c] = cmul(v[k1], s_tw[k1 * Tc + i]);
+            __syncthreads();
+#pragma unroll
+            for (int m = 0; m < Mc; m++)
+#pragma unroll
+                for (int ii = 0; ii < Tc; ii++) v[m * Tc + ii] = S[(i + Tc * m) * pitch + ii * 8 + c];
+#pragma unroll
+            for (int m = 0; m < Mc; m++) dft<float, Tc>(v + m * Tc, false);
+            if (p.mode == 2) {
+                const int64_t rel = (tile_ptr(w) - p.ws) % p.tile_elems;      // same offset inside the kernel spectrum tile
+                const cf *kp = p.kspec + rel + c;
+#pragma unroll
+                for (int m = 0; m < Mc; m++)
+#pragma unroll
+                    for (int k2 = 0; k2 < Tc; k2++) v[m * Tc + k2] = cmul(v[m * Tc + k2], ld_cf(kp + (int64_t)(i + Tc * m + E * k2) * p.inner));
+            }
+        } else {
+#pragma unroll
+            for (int m = 0; m < Mc; m++)
+#pragma unroll
+                for (int k2 = 0; k2 < Tc; k2++) v[m * Tc + k2] = S[(i + Tc * m + E * k2) * 8 + c];
+        }
+        if (p.mode == 0) {
+            __syncthreads();                               // all exchange reads done: S may be restaged
+            if (w + gridDim.x < p.nwork) prefetch(w + gridDim.x);
+#pragma unroll
+            for (int m = 0; m < Mc; m++)
+#pragma unroll
+                for (int k2 = 0; k2 < Tc; k2++) st_cf(gt + (int64_t)(i + Tc * m + E * k2) * p.inner, v[m * Tc + k2]);
+            continue;
+        }
+        if constexpr (Tc == E) {
+            // square case: the rows this thread holds (i + E k2) are also the rows the forward-structured flow starts from,
+            // so the inverse is the forward flow with conjugated twiddles (no transposed table needed)
+            dft<float, E>(v, true);
+            __syncthreads();                               // every thread has finished reading S
+#pragma unroll
+            for (int n1 = 0; n1 < E; n1++) S[n1 * pitch + i * 8 + c] = cmulc(v[n1], s_tw[n1 * Tc + i]);
+            __syncthreads();
+#pragma unroll
+            for (int ii = 0; ii < Tc; ii++) v[ii] = S[i * pitch + ii * 8 + c];
+            __syncthreads();
+        } else {
+            // ---- inverse: radix Tc over k2 -> conj twiddle -> exchange -> radix E over k1 -> rows i + Tc j ----
+#pragma unroll
+            for (int m = 0; m < Mc; m++) dft<float, Tc>(v + m * Tc, true);
+            __syncthreads();                               // every thread has finished reading S
+#pragma unroll
+            for (int m = 0; m < Mc; m++)
+#pragma unroll
+                for (int ii = 0; ii < Tc; ii++) S[(i + Tc * m) * pitch + ii * 8 + c] = cmulc(v[m * Tc + ii], s_twT[ii * E + (i + Tc * m)]);
+            __syncthreads();
+            // after the exchange thread i owns "time" index i of every k1 row
+#pragma unroll
+            for (int k1 = 0; k1 < E; k1++) v[k1] = S[k1 * pitch + i * 8 + c];
+            __syncthreads();
+        }
+        if (w + gridDim.x < p.nwork) prefetch(w + gridDim.x);
+        dft<float, E>(v, true);
+#pragma unroll
+        for (int j = 0; j < E; j++) st_cf(gt + (int64_t)(i + Tc * j) * p.inner, v[j]);
+    }
+}
+
+}  // namespace fast
+
+// kernel spectrum [rows][Hp] in natural bin order (bins 0..L, generic path) -> the fast path's row layout (pitch L + 8):
+// column 0 <- bin 0, column 1 <- bin L/2, columns (2s, 2s+1) <- bins (s, L-s), column L <- bin L (Nyquist), L+1.. <- 0.
+struct KfastParams {
+    const cx<float> *kspec;
+    cx<float> *kfast;
+    int64_t rows;
+    int L, Hp;
+};
+struct KfastBody {
+    static HD void run(const BlockCtx &c, const KfastParams &p)
+    {
+        const int pitch = p.L + fast::kPad;
+        const int64_t total = p.rows * pitch;
+        for (int64_t e = c.bid * c.nt + c.tid; e < total; e += c.nb * c.nt) {
+            const int64_t q = e / pitch;
+            const int pc = (int)(e % pitch);
+            cx<float> val = cx<float>{0.f, 0.f};
+            if (pc <= p.L) {
+                int bin;
+                if (pc == p.L) bin = p.L;
+                else if (pc == 0) bin = 0;
+                else if (pc == 1) bin = p.L / 2;
+                else bin = (pc & 1) ? p.L - (pc >> 1) : (pc >> 1);
+                val = p.kspec[q * p.Hp + bin];
+            }
+            p.kfast[e] = val;
+        }
+    }
+};
+}  // namespace ndc
+#endif  // NDCONV_CUDA
