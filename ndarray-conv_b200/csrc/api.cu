@@ -328,7 +328,7 @@ static int cap_col_axis(bool is_dbl) { return is_dbl ? 512 : 1024; }
 struct FftPlan {
     int N = 0;
     bool is_cx = false;
-    bool opt2d = false;           // sm_100a fast path: 2-D real f32, tile 1024 x 2048 (kernels_fft_opt.cuh)
+    bool fast = false;            // sm_100a fast path: real f32, rank 2 or 3, power-of-two tiles (kernels_fft_fast.cuh)
     AxisTiling tl[NDC_MAX_DIM];
     FftLen fl[NDC_MAX_DIM];       // complex transform per axis (last axis: F/2 for real input)
     int H = 0, Hp = 0;
@@ -376,14 +376,14 @@ static int make_plan(const Geom &g, FftPlan *pl)
     const int N = g.ndim;
     const bool is_cx = dtype_is_complex(g.dtype), is_dbl = (g.dtype == NDCONV_F64 || g.dtype == NDCONV_C64);
     pl->N = N; pl->is_cx = is_cx;
-    pl->opt2d = fast_eligible(g);
+    pl->fast = fast_eligible(g);
     for (int a = 0; a < N; a++) {
-        if (pl->opt2d) {
+        if (pl->fast) {
             static const int menu_last[4] = {256, 512, 1024, 2048}, menu_col[7] = {16, 32, 64, 128, 256, 512, 1024};
             pl->tl[a].F = 0;
             if (a == N - 1) fast_pick_tile(g.P[a], g.Kd[a], menu_last, 4, &pl->tl[a]);
             else fast_pick_tile(g.P[a], g.Kd[a], menu_col, 7, &pl->tl[a]);
-            if (pl->tl[a].F == 0) { pl->opt2d = false; a = -1; continue; }      // no usable tile: replan everything on the generic path
+            if (pl->tl[a].F == 0) { pl->fast = false; a = -1; continue; }      // no usable tile: replan everything on the generic path
             if (!factor_radices(a == N - 1 ? pl->tl[a].F / 2 : pl->tl[a].F, &pl->fl[a])) return NDCONV_ERR_INTERNAL;
             continue;
         }
@@ -988,7 +988,7 @@ static int conv_fft_t(ndconv_processor *p, const ndconv_problem *pr, PlanEntry *
     void *dev_out = out;
     if (pr->memory == NDCONV_MEM_HOST) { st = p->out_stage.reserve(obytes); if (st) return st; dev_out = p->out_stage.p; }
 #ifdef NDCONV_CUDA
-    if (pl.opt2d) {
+    if (pl.fast) {
         if constexpr (sizeof(R) == 4) {
             st = conv_fft_fast(p, pr, g, pl, ml, metabuf, dev_x, dev_out, kent); if (st) return st;
             if (pr->memory == NDCONV_MEM_HOST) {
