@@ -21,16 +21,18 @@
 // Reference stages replaced: conv_fft/padding.rs:30-62, processor/real.rs:105-154, mod.rs:268, real.rs:233-280, mod.rs:282-289.
 #pragma once
 #include "kernels_fft.h"
+#include "packed_cf.cuh"
 
 #ifdef NDCONV_CUDA
 namespace ndc {
 namespace fast {
 
 typedef cx<float> cf;
+typedef pk::pcf pc;              // the same 8 bytes as cf, held as one 64-bit register pair for FADD2 / FMUL2 / FFMA2 (packed_cf.cuh)
 constexpr int kPad = 8;          // extra columns per row: Nyquist + 7 zeros (keeps rows 64-byte aligned; 128-byte rows measured no faster)
 
-__device__ __forceinline__ cf ld_cf(const cf *p) { float2 t = *reinterpret_cast<const float2 *>(p); return cf{t.x, t.y}; }
-__device__ __forceinline__ void st_cf(cf *p, cf v) { *reinterpret_cast<float2 *>(p) = make_float2(v.re, v.im); }
+__device__ __forceinline__ pc ld_pc(const cf *p) { pc r; r.v = *reinterpret_cast<const unsigned long long *>(p); return r; }
+__device__ __forceinline__ void st_pc(cf *p, pc v) { *reinterpret_cast<unsigned long long *>(p) = v.v; }
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc)
 {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
@@ -108,17 +110,18 @@ __global__ void __launch_bounds__(128, 4) row_fwd(const __grid_constant__ RowPar
 {
     constexpr int L = RowCfg<T>::L, M = RowCfg<T>::M, G = RowCfg<T>::G;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    cf *s_tw = reinterpret_cast<cf *>(smem_raw);          // s_tw[k1 * T + t] = W_L^{t k1}
-    cf *s_twr = s_tw + L;                                 // w^k, k < L/2
-    cf *s_ex = s_twr + L / 2;
+    pc *s_tw = reinterpret_cast<pc *>(smem_raw);          // s_tw[k1 * T + t] = W_L^{t k1}
+    pc *s_twr = s_tw + L;                                 // (-i/2) w^k, k < L/2
+    pc *s_ex = s_twr + L / 2;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane / T, t = lane % T;
-    for (int idx = threadIdx.x; idx < L; idx += blockDim.x) s_tw[idx] = p.tw[(idx / T) * (idx % T)];
-    for (int idx = threadIdx.x; idx < L / 2; idx += blockDim.x) s_twr[idx] = p.twr[idx];
+    for (int idx = threadIdx.x; idx < L; idx += blockDim.x) s_tw[idx] = ld_pc(p.tw + (idx / T) * (idx % T));
+    for (int idx = threadIdx.x; idx < L / 2; idx += blockDim.x) { const cf w = p.twr[idx]; s_twr[idx] = pk::mk(0.5f * w.im, -0.5f * w.re); }
     __syncthreads();
-    cf *sb = s_ex + warp * RowCfg<T>::wstride + g * RowCfg<T>::gstride;
+    pc *sb = s_ex + warp * RowCfg<T>::wstride + g * RowCfg<T>::gstride;
     constexpr int al = N - 1;
     const int src_lane = g * T + ((T - t) % T);
+    const pc half = pk::mk(0.5f, 0.5f);
     const int64_t nwarp_items = (p.nwork + G - 1) / G;
     for (int64_t wi = (int64_t)blockIdx.x * 4 + warp; wi < nwarp_items; wi += (int64_t)gridDim.x * 4) {
         const RowSrcInfo ri = resolve_fwd_row<N>(p, wi * G + g, L);
@@ -130,18 +133,18 @@ __global__ void __launch_bounds__(128, 4) row_fwd(const __grid_constant__ RowPar
             }
             continue;
         }
-        cf v[32];
+        pc v[32];
         // a beyond-extent / zero row without a constant last axis is all zero -- but the last axis may still be a constant border
         const bool interior = ri.active && !ri.beyond && !ri.zero && !ri.has_const && p.xstr[al] == 1 && ri.cl0 >= p.pf[al] && ri.cl0 + 2 * L <= p.pf[al] + p.n[al];
         if (interior) {
             const float *src = p.x + ri.base + (ri.cl0 - p.pf[al]);
             if ((reinterpret_cast<uintptr_t>(src) & 7) == 0) {
-                const float2 *s2 = reinterpret_cast<const float2 *>(src);
+                const unsigned long long *s2 = reinterpret_cast<const unsigned long long *>(src);
 #pragma unroll
-                for (int j = 0; j < 32; j++) { const float2 q = __ldg(s2 + t + T * j); v[j] = cf{q.x, q.y}; }
+                for (int j = 0; j < 32; j++) v[j].v = __ldg(s2 + t + T * j);
             } else {
 #pragma unroll
-                for (int j = 0; j < 32; j++) { const int e = 2 * (t + T * j); v[j] = cf{__ldg(src + e), __ldg(src + e + 1)}; }
+                for (int j = 0; j < 32; j++) { const int e = 2 * (t + T * j); v[j] = pk::mk(__ldg(src + e), __ldg(src + e + 1)); }
             }
         } else {
             const bool beyond = ri.beyond;
@@ -164,12 +167,12 @@ __global__ void __launch_bounds__(128, 4) row_fwd(const __grid_constant__ RowPar
                     }
                     q[h] = val;
                 }
-                v[j] = cf{q[0], q[1]};
+                v[j] = pk::mk(q[0], q[1]);
             }
         }
-        dft32<float>(v, false);                                          // over j -> k1
+        pk::dft<false, 32>(v);                                           // over j -> k1
 #pragma unroll
-        for (int k1 = 0; k1 < 32; k1++) sb[k1 * (T + 1) + t] = cmul(v[k1], s_tw[k1 * T + t]);
+        for (int k1 = 0; k1 < 32; k1++) sb[k1 * (T + 1) + t] = pk::cmul(v[k1], s_tw[k1 * T + t]);
         __syncwarp();
 #pragma unroll
         for (int m = 0; m < M; m++)
@@ -177,29 +180,32 @@ __global__ void __launch_bounds__(128, 4) row_fwd(const __grid_constant__ RowPar
             for (int i = 0; i < T; i++) v[m * T + i] = sb[(t + T * m) * (T + 1) + i];
         __syncwarp();
 #pragma unroll
-        for (int m = 0; m < M; m++) dft<float, T>(v + m * T, false);      // v[m*T + k2] = Z[k], k = t + T m + 32 k2
-        // partner Z[L-k] and R2C post-processing; primaries are k2 < T/2 (k < L/2)
-        float4 *dst4 = reinterpret_cast<float4 *>(ri.dst);
+        for (int m = 0; m < M; m++) pk::dft<false, T>(v + m * T);         // v[m*T + k2] = Z[k], k = t + T m + 32 k2
+        // partner Z[L-k] and R2C post-processing; primaries are k2 < T/2 (k < L/2):
+        //   X[k] = E + w^k O,  X[L-k] = conj(E - w^k O),  2E = Z[k] + conj Z[L-k],  w^k O = (-i/2) w^k (Z[k] - conj Z[L-k])
+        ulonglong2 *dst4 = reinterpret_cast<ulonglong2 *>(ri.dst);
 #pragma unroll
         for (int m = 0; m < M; m++) {
 #pragma unroll
             for (int k2 = 0; k2 < T / 2; k2++) {
                 const int ia = (M - 1 - m) * T + (T - 1 - k2);                                    // lanes t > 0
                 const int ib = ((M - m) % M) * T + (m > 0 ? T - 1 - k2 : (k2 > 0 ? T - k2 : T / 2)); // lane t == 0 (own registers)
-                float px = __shfl_sync(0xffffffffu, v[ia].re, src_lane);
-                float py = __shfl_sync(0xffffffffu, v[ia].im, src_lane);
-                if (t == 0) { px = v[ib].re; py = v[ib].im; }
-                const cf zk = v[m * T + k2];
+                float px = __shfl_sync(0xffffffffu, pk::re(v[ia]), src_lane);
+                float py = __shfl_sync(0xffffffffu, pk::im(v[ia]), src_lane);
+                if (t == 0) { px = pk::re(v[ib]); py = pk::im(v[ib]); }
+                const pc zk = v[m * T + k2];
                 const int k = t + T * m + 32 * k2;
-                float4 o4;
+                ulonglong2 o4;
                 if (k == 0) {
-                    o4 = make_float4(zk.re + zk.im, 0.f, px, -py);                                 // X[0] ; X[L/2] = conj Z[L/2]
-                    if (ri.active) *reinterpret_cast<float4 *>(ri.dst + L) = make_float4(zk.re - zk.im, 0.f, 0.f, 0.f);   // Nyquist X[L]
+                    o4.x = pk::mk(pk::re(zk) + pk::im(zk), 0.f).v;                                 // X[0]
+                    o4.y = pk::mk(px, -py).v;                                                      // X[L/2] = conj Z[L/2]
+                    if (ri.active) *reinterpret_cast<float4 *>(ri.dst + L) = make_float4(pk::re(zk) - pk::im(zk), 0.f, 0.f, 0.f);   // Nyquist X[L]
                 } else {
-                    const cf E = cf{0.5f * (zk.re + px), 0.5f * (zk.im - py)};
-                    const cf O = cf{0.5f * (zk.im + py), -0.5f * (zk.re - px)};
-                    const cf tw = cmul(s_twr[k], O);
-                    o4 = make_float4(E.re + tw.re, E.im + tw.im, E.re - tw.re, -(E.im - tw.im));
+                    const pc cp = pk::mk(px, -py);
+                    const pc e2 = pk::add(zk, cp), d = pk::sub(zk, cp);
+                    const pc tw = pk::cmul(d, s_twr[k]);
+                    o4.x = pk::fma(e2, half, tw).v;
+                    o4.y = pk::conj(pk::fma(e2, half, pk::neg(tw))).v;
                 }
                 if (ri.active) dst4[k] = o4;
             }
@@ -247,16 +253,16 @@ __global__ void __launch_bounds__(128, 4) row_inv(const __grid_constant__ RowPar
 {
     constexpr int L = RowCfg<T>::L, M = RowCfg<T>::M, G = RowCfg<T>::G;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    cf *s_tw = reinterpret_cast<cf *>(smem_raw);          // TRANSPOSED for the inverse flow: s_tw[i * 32 + k1] = W_L^{i k1} (k1 is the lane-dependent index)
-    cf *s_twr = s_tw + L;
-    cf *s_ex = s_twr + L / 2;
+    pc *s_tw = reinterpret_cast<pc *>(smem_raw);          // TRANSPOSED for the inverse flow: s_tw[i * 32 + k1] = W_L^{i k1} (k1 is the lane-dependent index)
+    pc *s_twr = s_tw + L;                                 // i conj(w^k), k < L/2
+    pc *s_ex = s_twr + L / 2;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane / T, t = lane % T;
-    for (int idx = threadIdx.x; idx < L; idx += blockDim.x) s_tw[idx] = p.tw[(idx >> 5) * (idx & 31)];
-    for (int idx = threadIdx.x; idx < L / 2; idx += blockDim.x) s_twr[idx] = p.twr[idx];
+    for (int idx = threadIdx.x; idx < L; idx += blockDim.x) s_tw[idx] = ld_pc(p.tw + (idx >> 5) * (idx & 31));
+    for (int idx = threadIdx.x; idx < L / 2; idx += blockDim.x) { const cf w = p.twr[idx]; s_twr[idx] = pk::mk(w.im, w.re); }
     __syncthreads();
-    cf *sb = s_ex + warp * RowCfg<T>::wstride + g * RowCfg<T>::gstride;
-    float4 *sb4 = reinterpret_cast<float4 *>(s_ex + warp * RowCfg<T>::wstride) + g * (L / 2 + 1);  // staging: L/2 slots + the Nyquist column, linear
+    pc *sb = s_ex + warp * RowCfg<T>::wstride + g * RowCfg<T>::gstride;
+    ulonglong2 *sb4 = reinterpret_cast<ulonglong2 *>(s_ex + warp * RowCfg<T>::wstride) + g * (L / 2 + 1);  // staging: L/2 slots + the Nyquist column, linear
     constexpr int al = N - 1;
     const int src_lane = g * T + ((T - t) % T);
     const int64_t nwarp_items = (p.nwork + G - 1) / G;
@@ -266,7 +272,7 @@ __global__ void __launch_bounds__(128, 4) row_inv(const __grid_constant__ RowPar
     RowInvInfo ri = resolve_inv_row<N>(p, wi * G + g, L);
     auto stage = [&](const RowInvInfo &r) {
         if (r.active) {
-            const float4 *s4 = reinterpret_cast<const float4 *>(r.src);
+            const ulonglong2 *s4 = reinterpret_cast<const ulonglong2 *>(r.src);
 #pragma unroll
             for (int q = 0; q < 16; q++) cp_async16(sb4 + t + T * q, s4 + t + T * q);
             if (t == 0) cp_async16(sb4 + L / 2, s4 + L / 2);             // column L: the Nyquist bin
@@ -275,27 +281,29 @@ __global__ void __launch_bounds__(128, 4) row_inv(const __grid_constant__ RowPar
     };
     stage(ri);
     for (; wi < nwarp_items; wi += wstep) {
-        cf v[32], b[16];
+        pc v[32], b[16];
         cp_async_wait_all();
         __syncwarp();
-        const float nyq = sb4[L / 2].x;
-        // C2R pre-processing (x2): Z[k] = E + i O, Z[L-k] = conj(E) + i conj(O), E = Y[k] + conj Y[L-k], O = conj(w^k)(Y[k] - conj Y[L-k])
+        pc nq; nq.v = sb4[L / 2].x;
+        const float nyq = pk::re(nq);
+        // C2R pre-processing (x2): Z[k] = E + O', Z[L-k] = conj(E - O'), E = Y[k] + conj Y[L-k], O' = i conj(w^k) (Y[k] - conj Y[L-k])
 #pragma unroll
         for (int m = 0; m < M; m++) {
 #pragma unroll
             for (int k2 = 0; k2 < T / 2; k2++) {
                 const int k = t + T * m + 32 * k2;
-                const float4 q = sb4[k];
-                cf zk, zp;
+                const ulonglong2 q = sb4[k];
+                pc yk, ym; yk.v = q.x; ym.v = q.y;
+                pc zk, zp;
                 if (k == 0) {
-                    zk = cf{q.x + nyq, q.x - nyq};                              // Z[0] from the real DC / Nyquist bins
-                    zp = cf{2.f * q.z, -2.f * q.w};                             // Z[L/2] = 2 conj Y[L/2]
+                    zk = pk::mk(pk::re(yk) + nyq, pk::re(yk) - nyq);           // Z[0] from the real DC / Nyquist bins
+                    zp = pk::mk(2.f * pk::re(ym), -2.f * pk::im(ym));          // Z[L/2] = 2 conj Y[L/2]
                 } else {
-                    const cf E = cf{q.x + q.z, q.y - q.w};
-                    const cf D = cf{q.x - q.z, q.y + q.w};
-                    const cf O = cmulc(D, s_twr[k]);
-                    zk = cf{E.re - O.im, E.im + O.re};
-                    zp = cf{E.re + O.im, -E.im + O.re};
+                    const pc cm = pk::conj(ym);
+                    const pc E = pk::add(yk, cm), D = pk::sub(yk, cm);
+                    const pc O = pk::cmul(D, s_twr[k]);
+                    zk = pk::add(E, O);
+                    zp = pk::conj(pk::sub(E, O));
                 }
                 v[m * T + k2] = zk;
                 b[m * (T / 2) + k2] = zp;
@@ -309,26 +317,26 @@ __global__ void __launch_bounds__(128, 4) row_inv(const __grid_constant__ RowPar
             for (int k2r = T / 2; k2r < T; k2r++) {
                 const int ia = (M - 1 - mr) * (T / 2) + (T - 1 - k2r);                                            // source lanes t' > 0
                 const int ib = mr > 0 ? (M - mr) * (T / 2) + (T - 1 - k2r) : (k2r == T / 2 ? 0 : (T - k2r));      // lane 0: own b[]
-                float px = __shfl_sync(0xffffffffu, b[ia].re, src_lane);
-                float py = __shfl_sync(0xffffffffu, b[ia].im, src_lane);
-                if (t == 0) { px = b[ib].re; py = b[ib].im; }
-                v[mr * T + k2r] = cf{px, py};
+                float px = __shfl_sync(0xffffffffu, pk::re(b[ia]), src_lane);
+                float py = __shfl_sync(0xffffffffu, pk::im(b[ia]), src_lane);
+                if (t == 0) { px = pk::re(b[ib]); py = pk::im(b[ib]); }
+                v[mr * T + k2r] = pk::mk(px, py);
             }
         }
         // inverse: radix T over k2, conj twiddle, exchange, radix 32 over k1
 #pragma unroll
-        for (int m = 0; m < M; m++) dft<float, T>(v + m * T, true);
+        for (int m = 0; m < M; m++) pk::dft<true, T>(v + m * T);
 #pragma unroll
         for (int m = 0; m < M; m++)
 #pragma unroll
-            for (int i = 0; i < T; i++) sb[(t + T * m) * (T + 1) + i] = cmulc(v[m * T + i], s_tw[i * 32 + (t + T * m)]);
+            for (int i = 0; i < T; i++) sb[(t + T * m) * (T + 1) + i] = pk::cmulc(v[m * T + i], s_tw[i * 32 + (t + T * m)]);
         __syncwarp();
 #pragma unroll
         for (int k1 = 0; k1 < 32; k1++) v[k1] = sb[k1 * (T + 1) + t];
         __syncwarp();
         const RowInvInfo cur = ri;
         if (wi + wstep < nwarp_items) { ri = resolve_inv_row<N>(p, (wi + wstep) * G + g, L); stage(ri); }
-        dft32<float>(v, true);                                           // v[j] = z[t + T j] = (y[2n], y[2n+1]), n = t + T j
+        pk::dft<true, 32>(v);                                            // v[j] = z[t + T j] = (y[2n], y[2n+1]), n = t + T j
         if (!cur.active) continue;
         const int Kd1 = p.Kd[al];
         const int64_t mbase = (int64_t)cur.tl * p.V[al];
@@ -341,24 +349,25 @@ __global__ void __launch_bounds__(128, 4) row_inv(const __grid_constant__ RowPar
                 const int64_t o_lo = mbase + i - (Kd1 - 1);
                 const bool ok0 = i >= Kd1 - 1 && o_lo < p.O[al];
                 const bool ok1 = i + 1 >= Kd1 - 1 && o_lo + 1 < p.O[al];
-                if (vec_ok && ok0 && ok1) *reinterpret_cast<float2 *>(p.out + cur.orow + o_lo) = make_float2(v[j].re, v[j].im);
+                if (vec_ok && ok0 && ok1) *reinterpret_cast<unsigned long long *>(p.out + cur.orow + o_lo) = v[j].v;
                 else {
-                    if (ok0) p.out[cur.orow + o_lo] = v[j].re;
-                    if (ok1) p.out[cur.orow + o_lo + 1] = v[j].im;
+                    if (ok0) p.out[cur.orow + o_lo] = pk::re(v[j]);
+                    if (ok1) p.out[cur.orow + o_lo + 1] = pk::im(v[j]);
                 }
             }
         } else {
-            const int64_t s1 = p.s[al];
+            // positions along the last axis fit 32 bits (checked on the host); a stride larger than the axis keeps output 0 only
+            const uint32_t s1 = (uint32_t)(p.s[al] < 0x7fffffff ? p.s[al] : 0x7fffffff), O1 = (uint32_t)p.O[al];
 #pragma unroll
             for (int j = 0; j < 32; j++) {
 #pragma unroll
                 for (int h = 0; h < 2; h++) {
                     const int i = 2 * (t + T * j) + h;
                     if (i < Kd1 - 1) continue;
-                    const int64_t q = mbase + i - (Kd1 - 1);
-                    if (q % s1) continue;
-                    const int64_t o = q / s1;
-                    if (o < p.O[al]) p.out[cur.orow + o] = h ? v[j].im : v[j].re;
+                    const uint32_t q = (uint32_t)(mbase + i - (Kd1 - 1));
+                    const uint32_t o = q / s1;
+                    if (o * s1 != q) continue;
+                    if (o < O1) p.out[cur.orow + o] = h ? pk::im(v[j]) : pk::re(v[j]);
                 }
             }
         }
@@ -391,20 +400,24 @@ __global__ void __launch_bounds__(ColCfg<E, Tc>::threads, ColCfg<E, Tc>::min_blo
     using C = ColCfg<E, Tc>;
     constexpr int F = C::F, Mc = C::Mc, pitch = C::pitch;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    cf *s_tw = reinterpret_cast<cf *>(smem_raw);        // s_tw[k1 * Tc + i] = W_F^{i k1}, k1 < E, i < Tc   (forward: i is the thread index)
-    cf *s_twT = s_tw + F;                               // s_twT[ii * E + k1] = W_F^{ii k1}   (inverse, Tc != E: k1 is the thread-dependent index)
-    cf *S = s_tw + (Tc == E ? 1 : 2) * F;
+    pc *s_tw = reinterpret_cast<pc *>(smem_raw);        // s_tw[k1 * Tc + i] = W_F^{i k1}, k1 < E, i < Tc   (forward: i is the thread index)
+    pc *s_twT = s_tw + F;                               // s_twT[ii * E + k1] = W_F^{ii k1}   (inverse, Tc != E: k1 is the thread-dependent index)
+    pc *S = s_tw + (Tc == E ? 1 : 2) * F;
     const int tid = threadIdx.x;
     const int c = tid & 7, i = tid >> 3;                // column of the block, thread index inside the column (< Tc)
-    for (int idx = tid; idx < F; idx += C::threads) { s_tw[idx] = p.tw[(idx / Tc) * (idx % Tc)]; if (Tc != E) s_twT[idx] = p.tw[(idx / E) * (idx % E)]; }
-    const int64_t iblocks = p.inner / 8;
-    auto tile_ptr = [&](int64_t w) {
-        const int64_t ib = w % iblocks, o = (w / iblocks) % p.outer, tile = w / (iblocks * p.outer);
-        return p.ws + tile * p.tile_elems + o * (int64_t)F * p.inner + ib * 8;
+    for (int idx = tid; idx < F; idx += C::threads) { s_tw[idx] = ld_pc(p.tw + (idx / Tc) * (idx % Tc)); if (Tc != E) s_twT[idx] = ld_pc(p.tw + (idx / E) * (idx % E)); }
+    // work item -> (tile, outer index, 8-column block): 32-bit arithmetic (the host only takes this path when nwork < 2^31;
+    // a 64-bit division costs ~80 instructions), decoded ONCE per item: the prefetch of item w + gridDim.x hands its offsets on
+    const uint32_t iblocks = (uint32_t)(p.inner / 8), outer = (uint32_t)p.outer;
+    struct Item { int64_t off, rel; };           // element offset of the block's first column in ws ; the same inside one tile
+    auto decode = [&](int64_t w) {
+        const uint32_t w32 = (uint32_t)w, q = w32 / iblocks, ib = w32 - q * iblocks, tile = q / outer, o = q - tile * outer;
+        Item it; it.rel = (int64_t)o * F * p.inner + ib * 8; it.off = (int64_t)tile * p.tile_elems + it.rel;
+        return it;
     };
     constexpr int kChunks = (F * 4 + C::threads - 1) / C::threads;       // 16-byte chunks per thread
-    auto prefetch = [&](int64_t wn) {
-        const cf *gn = tile_ptr(wn);
+    auto prefetch = [&](const Item &it) {
+        const cf *gn = p.ws + it.off;
 #pragma unroll
         for (int m = 0; m < kChunks; m++) {
             const int id = tid + C::threads * m, row = id >> 2, part = id & 3;
@@ -412,10 +425,12 @@ __global__ void __launch_bounds__(ColCfg<E, Tc>::threads, ColCfg<E, Tc>::min_blo
         }
         cp_async_commit();
     };
-    if ((int64_t)blockIdx.x < p.nwork) prefetch(blockIdx.x);
+    Item nxt; nxt.off = 0; nxt.rel = 0;
+    if ((int64_t)blockIdx.x < p.nwork) { nxt = decode(blockIdx.x); prefetch(nxt); }
     for (int64_t w = blockIdx.x; w < p.nwork; w += gridDim.x) {
-        cf *gt = tile_ptr(w) + c;
-        cf v[E];
+        const Item cur = nxt;
+        cf *gt = p.ws + cur.off + c;
+        pc v[E];
         cp_async_wait_all();
         __syncthreads();
         if (p.mode != 1) {
@@ -423,23 +438,22 @@ __global__ void __launch_bounds__(ColCfg<E, Tc>::threads, ColCfg<E, Tc>::min_blo
 #pragma unroll
             for (int j = 0; j < E; j++) v[j] = S[(i + Tc * j) * 8 + c];
             __syncthreads();
-            dft<float, E>(v, false);
+            pk::dft<false, E>(v);
 #pragma unroll
-            for (int k1 = 0; k1 < E; k1++) S[k1 * pitch + i * 8 + c] = cmul(v[k1], s_tw[k1 * Tc + i]);
+            for (int k1 = 0; k1 < E; k1++) S[k1 * pitch + i * 8 + c] = pk::cmul(v[k1], s_tw[k1 * Tc + i]);
             __syncthreads();
 #pragma unroll
             for (int m = 0; m < Mc; m++)
 #pragma unroll
                 for (int ii = 0; ii < Tc; ii++) v[m * Tc + ii] = S[(i + Tc * m) * pitch + ii * 8 + c];
 #pragma unroll
-            for (int m = 0; m < Mc; m++) dft<float, Tc>(v + m * Tc, false);
+            for (int m = 0; m < Mc; m++) pk::dft<false, Tc>(v + m * Tc);
             if (p.mode == 2) {
-                const int64_t rel = (tile_ptr(w) - p.ws) % p.tile_elems;      // same offset inside the kernel spectrum tile
-                const cf *kp = p.kspec + rel + c;
+                const cf *kp = p.kspec + cur.rel + c;                           // same offset inside the kernel spectrum tile
 #pragma unroll
                 for (int m = 0; m < Mc; m++)
 #pragma unroll
-                    for (int k2 = 0; k2 < Tc; k2++) v[m * Tc + k2] = cmul(v[m * Tc + k2], ld_cf(kp + (int64_t)(i + Tc * m + E * k2) * p.inner));
+                    for (int k2 = 0; k2 < Tc; k2++) v[m * Tc + k2] = pk::cmul(v[m * Tc + k2], ld_pc(kp + (int64_t)(i + Tc * m + E * k2) * p.inner));
             }
         } else {
 #pragma unroll
@@ -449,20 +463,20 @@ __global__ void __launch_bounds__(ColCfg<E, Tc>::threads, ColCfg<E, Tc>::min_blo
         }
         if (p.mode == 0) {
             __syncthreads();                               // all exchange reads done: S may be restaged
-            if (w + gridDim.x < p.nwork) prefetch(w + gridDim.x);
+            if (w + gridDim.x < p.nwork) { nxt = decode(w + gridDim.x); prefetch(nxt); }
 #pragma unroll
             for (int m = 0; m < Mc; m++)
 #pragma unroll
-                for (int k2 = 0; k2 < Tc; k2++) st_cf(gt + (int64_t)(i + Tc * m + E * k2) * p.inner, v[m * Tc + k2]);
+                for (int k2 = 0; k2 < Tc; k2++) st_pc(gt + (int64_t)(i + Tc * m + E * k2) * p.inner, v[m * Tc + k2]);
             continue;
         }
         if constexpr (Tc == E) {
             // square case: the rows this thread holds (i + E k2) are also the rows the forward-structured flow starts from,
             // so the inverse is the forward flow with conjugated twiddles (no transposed table needed)
-            dft<float, E>(v, true);
+            pk::dft<true, E>(v);
             __syncthreads();                               // every thread has finished reading S
 #pragma unroll
-            for (int n1 = 0; n1 < E; n1++) S[n1 * pitch + i * 8 + c] = cmulc(v[n1], s_tw[n1 * Tc + i]);
+            for (int n1 = 0; n1 < E; n1++) S[n1 * pitch + i * 8 + c] = pk::cmulc(v[n1], s_tw[n1 * Tc + i]);
             __syncthreads();
 #pragma unroll
             for (int ii = 0; ii < Tc; ii++) v[ii] = S[i * pitch + ii * 8 + c];
@@ -470,22 +484,22 @@ __global__ void __launch_bounds__(ColCfg<E, Tc>::threads, ColCfg<E, Tc>::min_blo
         } else {
             // ---- inverse: radix Tc over k2 -> conj twiddle -> exchange -> radix E over k1 -> rows i + Tc j ----
 #pragma unroll
-            for (int m = 0; m < Mc; m++) dft<float, Tc>(v + m * Tc, true);
+            for (int m = 0; m < Mc; m++) pk::dft<true, Tc>(v + m * Tc);
             __syncthreads();                               // every thread has finished reading S
 #pragma unroll
             for (int m = 0; m < Mc; m++)
 #pragma unroll
-                for (int ii = 0; ii < Tc; ii++) S[(i + Tc * m) * pitch + ii * 8 + c] = cmulc(v[m * Tc + ii], s_twT[ii * E + (i + Tc * m)]);
+                for (int ii = 0; ii < Tc; ii++) S[(i + Tc * m) * pitch + ii * 8 + c] = pk::cmulc(v[m * Tc + ii], s_twT[ii * E + (i + Tc * m)]);
             __syncthreads();
             // after the exchange thread i owns "time" index i of every k1 row
 #pragma unroll
             for (int k1 = 0; k1 < E; k1++) v[k1] = S[k1 * pitch + i * 8 + c];
             __syncthreads();
         }
-        if (w + gridDim.x < p.nwork) prefetch(w + gridDim.x);
-        dft<float, E>(v, true);
+        if (w + gridDim.x < p.nwork) { nxt = decode(w + gridDim.x); prefetch(nxt); }
+        pk::dft<true, E>(v);
 #pragma unroll
-        for (int j = 0; j < E; j++) st_cf(gt + (int64_t)(i + Tc * j) * p.inner, v[j]);
+        for (int j = 0; j < E; j++) st_pc(gt + (int64_t)(i + Tc * j) * p.inner, v[j]);
     }
 }
 
