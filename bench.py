@@ -49,15 +49,18 @@ def metric_name():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe).  nvidia-smi needs ~0.1 s to
+    start, longer than a short timed region, so the sampler is started before the warm-up and the rows that arrive between
+    mark_begin() and mark_end() are the ones reported."""
     Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index=0):
         self.index, self.rows, self.proc = index, [], None
+        self.i0 = self.i1 = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(self.index)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -68,25 +71,36 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
+    def mark_begin(self):
+        self.i0 = len(self.rows)
+
+    def mark_end(self):
+        self.i1 = len(self.rows)
+
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.05)          # one more sampling period: the row that covers the end of the region
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        i0 = self.i0 if self.i0 is not None else 0
+        i1 = (self.i1 if self.i1 is not None else len(self.rows)) + 1
+        rows = self.rows[i0:i1] or self.rows[-1:]
+        sm = [float(r[1]) for r in rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        pw = [float(r[3]) for r in rows if len(r) >= 8 and r[3].replace(".", "").isdigit()]
         reasons = set()
-        for r in self.rows:
+        for r in rows:
             if len(r) < 8:
                 continue
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "power_w_max": max(pw) if pw else None}
 
 
 def peaks():
@@ -214,12 +228,13 @@ def run_gpu(args, w, rank, world, local_rank):
     spot = spot_check(xv, k_host, y_dev, slab_pf, int(pads[1][0]), w["padding"], dil, rows, n1)
 
     # ---- value: device-resident, CUDA events ----
-    for _ in range(max(args.warmup, 3)):
-        step_device()
-    barrier()
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    barrier()
+    clocks.mark_begin()
     l0 = proc.launch_count
     lib.c.ndconv_processor_set_profiling(proc.handle, 1)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -228,6 +243,7 @@ def run_gpu(args, w, rank, world, local_rank):
         step_device()
     e1.record(stream)
     barrier()
+    clocks.mark_end()
     ms = e0.elapsed_time(e1)
     launches = proc.launch_count - l0
     kprof = read_profile(lib, proc)
@@ -245,15 +261,17 @@ def run_gpu(args, w, rank, world, local_rank):
     def step_host():
         pr, keep = pkg.make_problem((rows, n1), (n1, 1), x_pin.data_ptr(), np.float32, kwd, mode, pmode, pkg.MEM_HOST, lib, explicit=explicit)
         lib.check(lib.c.ndconv_conv_fft(proc.handle, pr, y_pin.data_ptr()))
-    import ctypes  # noqa
-    step_host()
     e2e_steps = max(1, min(args.steps, 5))
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
+    if args.no_e2e:
+        e2e_steps, t_e2e = 0, float("nan")
+    else:
         step_host()
-    barrier()
-    t_e2e = (time.perf_counter() - t0) / e2e_steps
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            step_host()
+        barrier()
+        t_e2e = (time.perf_counter() - t0) / e2e_steps
     t_e = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
@@ -437,6 +455,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true", help="kernel experiments only: skip the host-buffer leg (the line then has no valid e2e)")
     ap.add_argument("--no-shapes", action="store_true", help="skip the secondary per-shape numbers (configs c1-c4)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
