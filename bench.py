@@ -38,9 +38,12 @@ WORKLOADS = {
     # name: (x shape, k shape, dilation, mode, padding)
     "c5": dict(x=(32768, 32768), k=(63, 63), dil=1, mode="full", padding="reflect", dtype="float32",
                desc="2D conv_fft f32 x=(32768,32768) k=(63,63) Full Reflect (BASELINE configs[4])"),
-    "c5s": dict(x=(8192, 8192), k=(63, 63), dil=1, mode="full", padding="reflect", dtype="float32",
+    "c5s": dict(x=(8192, 9868), k=(63, 63), dil=1, mode="full", padding="reflect", dtype="float32",
                 desc="reduced c5 for quick checks (NOT the headline)"),
 }
+# one tile-row stripes of c5 (experiments on L2 residency of the workspace; NOT bench lines)
+for _n, _r in (("s1024", 900), ("s512", 388), ("s256", 132)):
+    WORKLOADS[_n] = dict(x=(_r, 32768), k=(63, 63), dil=1, mode="full", padding="reflect", dtype="float32", desc=f"one {_n[1:]}-row tile stripe of c5 (experiment)")
 CPU_SAMPLE_ROWS = 4096   # rows of x in the bounded CPU sample
 
 
@@ -422,10 +425,11 @@ def read_profile(lib, proc):
 
 
 def measured_traffic(workload):
-    """per-launch DRAM traffic of each kernel from the committed ncu capture (profiles/r01_traffic_<workload>.json)"""
-    p = ROOT / "profiles" / f"r01_traffic_{workload}.json"
-    if not p.exists():
+    """per-launch DRAM traffic of each kernel from the latest committed ncu capture (profiles/r*_traffic_<workload>.json)"""
+    cands = sorted((ROOT / "profiles").glob(f"r*_traffic_{workload}.json"))
+    if not cands:
         return {}
+    p = cands[-1]
     return {k: v["traffic_bytes"] for k, v in json.loads(p.read_text())["kernels"].items()}
 
 
