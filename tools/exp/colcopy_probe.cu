@@ -62,14 +62,35 @@ template <int W, int MODE, int ORDER = 0> static void run(uint4 *ws, int ntiles,
     }
 }
 
-int main()
+int main(int argc, char **argv)
 {
     cudaDeviceProp pr; cudaGetDeviceProperties(&pr, 0);
     const int nsm = pr.multiProcessorCount;
+    const int ntiles = 300;                                   // ~2.5 GB
+    uint4 *ws, *sink; cudaMalloc(&ws, (size_t)ntiles * 1024 * 16384); cudaMalloc(&sink, 4096);
+    cudaMemset(ws, 0, (size_t)ntiles * 1024 * 16384);
+    if (argc > 1) {
+        // row pitch sweep: does the mapping of the 64-byte segments of consecutive rows onto DRAM channels / banks matter?
+        const int64_t pitches[] = {8256, 8320, 8448, 8704, 9216, 10240, 12288, 16384, 8192};
+        for (int64_t pb : pitches) {
+            printf("pitch %lld bytes: ", (long long)pb);
+            const int iblocks = 129;
+            const int64_t nwork = (int64_t)ntiles * iblocks, tile_bytes = 1024 * pb;
+            cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+            colcopy<64, 0, 0><<<nsm * 2, 256>>>(ws, tile_bytes, pb, iblocks, nwork, sink);
+            cudaDeviceSynchronize();
+            float best = 1e30f;
+            for (int r = 0; r < 3; r++) {
+                cudaEventRecord(e0);
+                colcopy<64, 0, 0><<<nsm * 2, 256>>>(ws, tile_bytes, pb, iblocks, nwork, sink);
+                cudaEventRecord(e1); cudaEventSynchronize(e1);
+                float ms; cudaEventElapsedTime(&ms, e0, e1); best = ms < best ? ms : best;
+            }
+            printf("64-byte segments, read+write, 2 CTAs/SM: %.3f ms  %.0f GB/s\n", best, (double)nwork * 1024 * 64 * 2 / (best * 1e-3) / 1e9);
+        }
+        return 0;
+    }
     const int64_t pitch_bytes = 1032 * 8, tile_bytes = 1024 * pitch_bytes;
-    const int ntiles = 300;                                   // 2.5 GB
-    uint4 *ws, *sink; cudaMalloc(&ws, (size_t)ntiles * tile_bytes); cudaMalloc(&sink, 4096);
-    cudaMemset(ws, 0, (size_t)ntiles * tile_bytes);
     printf("%s, %d SMs; %d tiles of 1024 rows x %lld bytes\n", pr.name, nsm, ntiles, (long long)pitch_bytes);
     run<64, 0>(ws, ntiles, tile_bytes, pitch_bytes, nsm, sink);
     run<64, 0, 1>(ws, ntiles, tile_bytes, pitch_bytes, nsm, sink);
