@@ -884,24 +884,14 @@ template <int E, int Tc> static void launch_col_t(const fast::ColParams &cp, int
     const int grid = (int)std::min<int64_t>(cp.nwork, (int64_t)num_sms * std::max(C::min_blocks, std::min(per_sm, 2048 / C::threads)));
     fast::col_pass<E, Tc><<<grid, C::threads, C::smem, stm>>>(cp);
 }
-template <int E> static void launch_col_sq(const fast::ColParams &cp, int num_sms, stream_t stm)
-{
-    using C = fast::ColSqCfg<E>;
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(fast::col_sq<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::smem); attr = true; }
-    const int per_sm = std::max(1, std::min(16, (int)((200 * 1024) / C::smem)));
-    const int grid = (int)std::min<int64_t>(cp.nwork, (int64_t)num_sms * std::max(C::min_blocks, std::min(per_sm, 2048 / C::threads)));
-    fast::col_sq<E><<<grid, C::threads, C::smem, stm>>>(cp);
-}
 static void launch_col(int F, const fast::ColParams &cp, int num_sms, stream_t stm)
 {
-    static const bool old_sq = getenv("NDCONV_COL_PADDED") != nullptr;      // experiments: the padded-pitch kernel for square tiles too
     switch (F) {
-    case 1024: if (old_sq) launch_col_t<32, 32>(cp, num_sms, stm); else launch_col_sq<32>(cp, num_sms, stm); break;
+    case 1024: launch_col_t<32, 32>(cp, num_sms, stm); break;
     case 512: launch_col_t<32, 16>(cp, num_sms, stm); break;
-    case 256: if (old_sq) launch_col_t<16, 16>(cp, num_sms, stm); else launch_col_sq<16>(cp, num_sms, stm); break;
+    case 256: launch_col_t<16, 16>(cp, num_sms, stm); break;
     case 128: launch_col_t<16, 8>(cp, num_sms, stm); break;
-    case 64: if (old_sq) launch_col_t<8, 8>(cp, num_sms, stm); else launch_col_sq<8>(cp, num_sms, stm); break;
+    case 64: launch_col_t<8, 8>(cp, num_sms, stm); break;
     case 32: launch_col_t<8, 4>(cp, num_sms, stm); break;
     default: launch_col_t<8, 2>(cp, num_sms, stm); break;
     }

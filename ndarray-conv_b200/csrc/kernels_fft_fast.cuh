@@ -516,108 +516,6 @@ __global__ void __launch_bounds__(ColCfg<E, Tc>::threads, ColCfg<E, Tc>::min_blo
     }
 }
 
-// ---- column pass, square tiles F = E * E: in-place swizzled exchange -------------------------------------------------------------
-// The staged item, both exchanges and nothing else live in ONE buffer of exactly F x 8 complex, viewed as an E x E matrix of
-// 8-column groups: entry (r, q) at  r * E * 8 + ((q ^ f(r)) * 8) + column,  f(r) = (r >> 1) & 1.  Global row R = q + E r of the item is
-// staged at entry (r, q).  Every exchange is a transposition in which a thread WRITES only entries it has itself just read
-// (thread i owns column i of the matrix in one phase and row i in the next), so no barrier separates the loads, the butterflies and
-// the stores of a phase and they overlap inside each warp (the padded-pitch kernel above spends FP-pipe time, shared-memory time and
-// load latency back to back: ~11 000 cycles per item per SM against 3 900 of FP work).  The XOR keeps every warp access at the
-// two-wavefront floor of a 256-byte request: four thread indices i per warp, rows 64 E bytes apart, pairs split over the two halves
-// of the 128-byte bank line.
-template <int E> struct ColSqCfg {
-    static constexpr int F = E * E, threads = E * 8;
-    static constexpr int smem = (F + F * 8) * 8;                         // twiddle table + the buffer
-    static constexpr int min_blocks = E == 32 ? 2 : 4;
-};
-
-template <int E>
-__global__ void __launch_bounds__(ColSqCfg<E>::threads, ColSqCfg<E>::min_blocks) col_sq(const __grid_constant__ ColParams p)
-{
-    using C = ColSqCfg<E>;
-    constexpr int F = C::F;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    pc *s_tw = reinterpret_cast<pc *>(smem_raw);        // s_tw[k1 * E + i] = W_F^{i k1}
-    pc *G = s_tw + F;
-    const int tid = threadIdx.x;
-    const int c = tid & 7, i = tid >> 3;                // column of the block, thread index inside the column (< E)
-    for (int idx = tid; idx < F; idx += C::threads) s_tw[idx] = ld_pc(p.tw + (idx / E) * (idx % E));
-    auto at = [&](int r, int q) { return r * (E * 8) + ((q ^ ((r >> 1) & 1)) * 8) + c; };      // entry (r, q), this thread's column
-    const uint32_t iblocks = (uint32_t)(p.inner / 8), outer = (uint32_t)p.outer;
-    struct Item { int64_t off, rel; };
-    auto decode = [&](int64_t w) {
-        const uint32_t w32 = (uint32_t)w, q = w32 / iblocks, ib = w32 - q * iblocks, tile = q / outer, o = q - tile * outer;
-        Item it; it.rel = (int64_t)o * F * p.inner + ib * 8; it.off = (int64_t)tile * p.tile_elems + it.rel;
-        return it;
-    };
-    constexpr int kChunks = (F * 4 + C::threads - 1) / C::threads;       // 16-byte chunks per thread
-    const uint64_t pol_keep = l2_policy_evict_last();
-    auto prefetch = [&](const Item &it) {
-        const cf *gn = p.ws + it.off;
-#pragma unroll
-        for (int m = 0; m < kChunks; m++) {
-            const int id = tid + C::threads * m, row = id >> 2, part = id & 3;      // global row `row` = q + E r
-            const int r = row / E, q = row % E;
-            if (F * 4 % C::threads == 0 || id < F * 4) cp_async16(G + r * (E * 8) + ((q ^ ((r >> 1) & 1)) * 8) + part * 2, gn + (int64_t)row * p.inner + part * 2);
-        }
-        cp_async_commit();
-    };
-    Item nxt; nxt.off = 0; nxt.rel = 0;
-    if ((int64_t)blockIdx.x < p.nwork) { nxt = decode(blockIdx.x); prefetch(nxt); }
-    for (int64_t w = blockIdx.x; w < p.nwork; w += gridDim.x) {
-        const Item cur = nxt;
-        cf *gt = p.ws + cur.off + c;
-        const bool more = w + gridDim.x < p.nwork;
-        if (more) nxt = decode(w + gridDim.x);
-        pc v[E];
-        cp_async_wait_all();
-        __syncthreads();                                   // the staged item is visible
-        // phase A: column i of the matrix = rows i + E j of the item
-#pragma unroll
-        for (int j = 0; j < E; j++) v[j] = G[at(j, i)];
-        if (p.mode != 1) {
-            pk::dft<false, E>(v);
-#pragma unroll
-            for (int k1 = 0; k1 < E; k1++) G[at(k1, i)] = pk::cmul(v[k1], s_tw[k1 * E + i]);
-            __syncthreads();
-            // phase B: row i of the matrix
-#pragma unroll
-            for (int ii = 0; ii < E; ii++) v[ii] = G[at(i, ii)];
-            pk::dft<false, E>(v);                           // v[k2] = row i + E k2 of the spectrum
-            if (p.mode == 0) {
-                __syncthreads();                            // every thread has read its row: the buffer may be restaged
-                if (more) prefetch(nxt);
-#pragma unroll
-                for (int k2 = 0; k2 < E; k2++) st_pc(gt + (int64_t)(i + E * k2) * p.inner, v[k2]);
-                continue;
-            }
-            const cf *kp = p.kspec + cur.rel + c;           // same offset inside the kernel spectrum tile
-#pragma unroll
-            for (int k2 = 0; k2 < E; k2++) v[k2] = pk::cmul(v[k2], ld_pc_keep(kp + (int64_t)(i + E * k2) * p.inner, pol_keep));
-            pk::dft<true, E>(v);                            // over k2 -> n1
-#pragma unroll
-            for (int n1 = 0; n1 < E; n1++) G[at(i, n1)] = pk::cmulc(v[n1], s_tw[n1 * E + i]);      // back into row i
-            __syncthreads();
-            // phase C: column i again
-#pragma unroll
-            for (int ii = 0; ii < E; ii++) v[ii] = G[at(ii, i)];
-        } else {
-            // inverse only: the thread holds rows i + E k2; transform, write its column, read its row
-            pk::dft<true, E>(v);
-#pragma unroll
-            for (int n1 = 0; n1 < E; n1++) G[at(n1, i)] = pk::cmulc(v[n1], s_tw[n1 * E + i]);
-            __syncthreads();
-#pragma unroll
-            for (int ii = 0; ii < E; ii++) v[ii] = G[at(i, ii)];
-        }
-        __syncthreads();                                    // every thread has read: the buffer may be restaged
-        if (more) prefetch(nxt);
-        pk::dft<true, E>(v);
-#pragma unroll
-        for (int j = 0; j < E; j++) st_pc(gt + (int64_t)(i + E * j) * p.inner, v[j]);
-    }
-}
-
 }  // namespace fast
 
 // kernel spectrum [rows][Hp] in natural bin order (bins 0..L, generic path) -> the fast path's row layout (pitch L + 8):
