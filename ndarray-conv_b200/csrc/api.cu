@@ -422,8 +422,47 @@ struct PlanEntry {
     MetaLayout ml;
     int ntap = 0;
     FftPlan pl;
+    // axis-0 split (plan_axis0_split): outputs [0, split_out) come from a sub-convolution whose tiles fit exactly, the rest
+    // from a second one that the planner gives a shorter tile -- instead of a whole last tile that is mostly padding
+    int64_t split_out = 0;
 };
 void PlanEntryDeleter::operator()(PlanEntry *e) const { if (e) { e->meta.release(); delete e; } }
+
+// Overlap-save along axis 0 works just as well across two launches as across the tiles of one (the identity the multi-GPU
+// slabs use).  When the last axis-0 tile of a fast-path plan is mostly padding -- 32830 output rows =
+// 34 x 962 + 122 on c5; 4104 = 4 x 962 + 256 per rank on 8 GPUs -- the problem is cut after the last full tile: part A
+// tiles exactly, part B gets whatever shorter tile the planner picks for it (both run on the device copy of the input).  A Circular
+// border on axis 0 reads from the far end of the array, which a part does not hold, so it is never split.
+static void plan_axis0_split(const ndconv_problem *pr, const Geom &g, const FftPlan &pl, PlanEntry *e)
+{
+    e->split_out = 0;
+#ifdef NDCONV_CUDA
+    static const bool disabled = getenv("NDCONV_DISABLE_SPLIT") != nullptr;
+    if (disabled || !pl.fast) return;
+    const AxisTiling &t = pl.tl[0];
+    if (t.ntiles < 2) return;
+    if ((g.bf[0] == NDCONV_BORDER_CIRCULAR && g.pf[0] > 0) || (g.bb[0] == NDCONV_BORDER_CIRCULAR && g.pb[0] > 0)) return;
+    const int64_t covered = (int64_t)(t.ntiles - 1) * t.V;                  // padded positions whose outputs the full tiles produce
+    const int64_t o_split = (covered + g.s[0] - 1) / g.s[0];
+    if (o_split <= 0 || o_split >= g.O[0]) return;
+    const int64_t pB = o_split * g.s[0];                                    // first padded row part B reads
+    const int64_t rowsA = covered + g.Kd[0] - 1 - g.pf[0];                  // input rows of part A (its back pad is 0)
+    if (pB < g.pf[0] || rowsA < 1 || rowsA > g.n[0]) return;                // the cut must fall inside the array on both sides
+    const int64_t rowsB = g.n[0] - (pB - g.pf[0]);
+    if (rowsB < 1 || g.pb[0] >= rowsB || g.pf[0] >= rowsA) return;          // a border may not reach past the part that carries it
+    static const int menu_col[7] = {16, 32, 64, 128, 256, 512, 1024};
+    AxisTiling tb; tb.F = 0;
+    fast_pick_tile(g.P[0] - pB, g.Kd[0], menu_col, 7, &tb);
+    if (tb.F == 0) return;
+    const int64_t full = (int64_t)t.ntiles * t.F, split = (int64_t)(t.ntiles - 1) * t.F + (int64_t)tb.ntiles * tb.F;
+    double samples = 1.0;
+    for (int a = 0; a < g.ndim; a++) samples *= (double)g.P[a];
+    if (samples < 4.0e6 || (full - split) * 64 < full) return;              // three more launches must buy at least 1.5 % of the rows
+    e->split_out = o_split;
+#else
+    (void)pr; (void)g; (void)pl;
+#endif
+}
 
 static int get_plan_entry(ndconv_processor *p, const ndconv_problem *pr, int path, PlanEntry **out)
 {
@@ -479,6 +518,7 @@ static int get_plan_entry(ndconv_processor *p, const ndconv_problem *pr, int pat
         st = upload_meta(p, ent->meta, g, maps, &taps, &ent->ml); if (st) return st;
     } else {
         st = make_plan(g, &ent->pl); if (st) return st;
+        plan_axis0_split(pr, g, ent->pl, ent.get());
         st = upload_meta(p, ent->meta, g, maps, nullptr, &ent->ml); if (st) return st;
     }
     st = be_sync(p->stream); if (st) return st;      // the staging vector of upload_meta dies here
@@ -969,6 +1009,8 @@ static int conv_fft_fast(ndconv_processor *p, const ndconv_problem *pr, const Ge
 }
 #endif
 
+static int conv_fft_impl(ndconv_processor *p, const ndconv_problem *pr, void *out);
+
 template <class R>
 static int conv_fft_t(ndconv_processor *p, const ndconv_problem *pr, PlanEntry *pe, void *out)
 {
@@ -978,6 +1020,32 @@ static int conv_fft_t(ndconv_processor *p, const ndconv_problem *pr, PlanEntry *
     int st;
     const void *dev_x = nullptr;
     st = stage_input2(p, pr, *pe, &dev_x); if (st) return st;
+    if (pe->split_out > 0) {
+        // two device-resident sub-convolutions along axis 0 (plan_axis0_split); each has its own cached plan
+        const Geom gc = pe->g;                      // copies: the nested calls may evict this entry
+        const int64_t o_split = pe->split_out, pB = o_split * gc.s[0];
+        const int64_t rowsA = (int64_t)(pe->pl.tl[0].ntiles - 1) * pe->pl.tl[0].V + gc.Kd[0] - 1 - gc.pf[0];
+        const size_t obytes = (size_t)gc.out_total * gc.es;
+        void *dev_out = out;
+        if (pr->memory == NDCONV_MEM_HOST) { st = p->out_stage.reserve(obytes); if (st) return st; dev_out = p->out_stage.p; }
+        int64_t out_row = 1;
+        for (int a = 1; a < N; a++) out_row *= gc.O[a];
+        ndconv_problem base = *pr;
+        base.memory = NDCONV_MEM_DEVICE; base.data = dev_x;
+        for (int a = 0; a < N; a++) base.data_strides[a] = gc.xstr[a];
+        ndconv_problem sub = base;
+        sub.data_shape[0] = rowsA; sub.pad[0][1] = 0; sub.border[0][1].type = NDCONV_BORDER_ZEROS;
+        st = conv_fft_impl(p, &sub, dev_out); if (st) return st;
+        sub = base;
+        sub.data = (const char *)dev_x + (pB - gc.pf[0]) * gc.xstr[0] * (int64_t)gc.es;
+        sub.data_shape[0] = gc.n[0] - (pB - gc.pf[0]); sub.pad[0][0] = 0; sub.border[0][0].type = NDCONV_BORDER_ZEROS;
+        st = conv_fft_impl(p, &sub, (char *)dev_out + (size_t)o_split * (size_t)out_row * gc.es); if (st) return st;
+        if (pr->memory == NDCONV_MEM_HOST) {
+            st = be_d2h(out, dev_out, obytes, p->stream); if (st) return st;
+            st = be_sync(p->stream); if (st) return st;
+        }
+        return NDCONV_OK;
+    }
     const MetaLayout &ml = pe->ml;
     DevBuf &metabuf = pe->meta;
     const cx<R> *kspec = nullptr;

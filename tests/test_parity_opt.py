@@ -29,6 +29,12 @@ CASES = [
     ((20, 70, 300), (3, 4, 5), 1, "full", ("custom", ["reflect", "circular", ("const", 0.5)]), False),
     ((40, 300, 130), (2, 3, 9), 2, ("custom", [1, 0, 5], [2, 1, 3]), "replicate", True),
     ((300, 20, 520), (9, 3, 3), 1, "same", ("explicit", [["zeros", "reflect"], ["replicate", "circular"], ["reflect", "zeros"]]), True),
+    # axis-0 split (plan_axis0_split): the last axis-0 tile would be mostly padding, so the rows are cut into two sub-convolutions
+    ((1100, 4000), (5, 9), 1, "same", "reflect", True),
+    ((1100, 4000), (5, 9), 1, ("custom", [2, 4], [3, 2]), "replicate", False),                 # strided outputs across the cut
+    ((1100, 4000), (5, 9), 2, "full", ("custom", [("const", 0.75), "circular"]), True),
+    ((1100, 4000), (5, 9), 1, "same", ("custom", ["circular", "reflect"]), True),             # Circular on axis 0: never split
+    ((600, 40, 300), (5, 3, 3), 1, "same", ("const", 0.25), True),                             # rank 3
 ]
 
 
