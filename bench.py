@@ -44,6 +44,7 @@ WORKLOADS = {
 # one tile-row stripes of c5 (experiments on L2 residency of the workspace; NOT bench lines)
 for _n, _r in (("s1024", 900), ("s512", 388), ("s256", 132)):
     WORKLOADS[_n] = dict(x=(_r, 32768), k=(63, 63), dil=1, mode="full", padding="reflect", dtype="float32", desc=f"one {_n[1:]}-row tile stripe of c5 (experiment)")
+WORKLOADS["r8"] = dict(x=(4104, 32768), k=(63, 63), dil=1, mode="full", padding="reflect", dtype="float32", desc="one rank's share of c5 on 8 GPUs (experiment)")
 CPU_SAMPLE_ROWS = 4096   # rows of x in the bounded CPU sample
 
 

@@ -403,7 +403,7 @@ template <int E, int Tc> struct ColCfg {
     static constexpr int pitch = Tc * 8 + 8;                             // padded k1-row stride of the exchange buffer
     static constexpr int ex = (E * pitch > F * 8 ? E * pitch : F * 8);
     static constexpr int smem = ((Tc == E ? 1 : 2) * F + ex) * 8;         // forward table, transposed table for the inverse when Tc != E, exchange buffer
-    static constexpr int min_blocks = E == 32 ? (Tc == 32 ? 2 : 3) : 4;
+    static constexpr int min_blocks = (E == 32 && Tc == 32) ? 2 : 4;      // 512-row tiles: 4 CTAs of 128 threads at 126 registers beat 3 at 168 (s512: 52 -> 48 us)
 };
 
 template <int E, int Tc>
