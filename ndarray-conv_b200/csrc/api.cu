@@ -633,7 +633,7 @@ static int try_direct_tile(ndconv_processor *p, const ndconv_problem *pr, const 
     while (elems * es > budget && TO1 > 1) { TO1 >>= 1; elems = shape(TO0, TO1, TO2); }
     while (elems * es > budget && TO2 > 1) { TO2 >>= 1; elems = shape(TO0, TO1, TO2); }
     if (elems * es > budget) return NDCONV_OK;
-    const size_t tap_bytes = align_up((size_t)e.ntap * es, 16) + (size_t)e.ntap * 4;
+    const size_t tap_bytes = align_up((size_t)e.ntap * es, 16) + (size_t)e.ntap * 4 + (size_t)(tp.IT[0] + tp.IT[1] + tp.IT2p) * 4;   // taps + the window's border maps
     const size_t tile_bytes = align_up((size_t)elems * es, 128);
     if (tile_bytes + tap_bytes + 256 > 190 * 1024) return NDCONV_OK;
     tp.tile_elems = (int)elems;

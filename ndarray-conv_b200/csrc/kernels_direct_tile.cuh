@@ -12,11 +12,12 @@
 //     part; only the halo elements that fall outside the array are then patched through the border index maps
 //     (index arithmetic, a few % of the tile) -- the padded array of src/padding/mod.rs:84-117 is never materialised.
 //     Without TMA (1/2/16-byte elements, unaligned rows) the whole window is gathered through the maps.
-// The compacted tap list (gen_offset_list, src/dilation/mod.rs:34-60) lives in shared memory as (tile offset, weight);
+// The compacted tap list (gen_offset_list, src/dilation/mod.rs:34-60) lives in shared memory as (byte offset in the tile, weight);
 // each thread keeps TO0 accumulators in registers and walks the taps in the reference's order with un-fused
 // multiply/add, so results stay bit-identical (integers wrap, floats round identically).
 #pragma once
 #include "kernels_direct.h"
+#include <climits>
 
 #ifdef NDCONV_CUDA
 #include <cuda.h>
@@ -46,20 +47,36 @@ struct TileParams {
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-template <class T> __device__ __forceinline__ T tile_padded_at(const TileParams &p, const int64_t *c)
+// tile element at a 32-bit shared-memory address.  The tap loop addresses the tile as base + offset with the base converted ONCE:
+// through a generic pointer ptxas re-derived the shared window (S2UR CgaCtaId / ULEA) for every access -- 9 instructions per
+// multiply-add instead of 3 (ncu source page, c4).
+template <int BYTES> struct LdsRaw;
+template <> struct LdsRaw<1> { typedef uint8_t V; static __device__ __forceinline__ V ld(uint32_t a) { uint16_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=h"(v) : "r"(a)); return (V)v; } };
+template <> struct LdsRaw<2> { typedef uint16_t V; static __device__ __forceinline__ V ld(uint32_t a) { uint16_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a)); return v; } };
+template <> struct LdsRaw<4> { typedef uint32_t V; static __device__ __forceinline__ V ld(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; } };
+template <> struct LdsRaw<8> { typedef uint64_t V; static __device__ __forceinline__ V ld(uint32_t a) { uint64_t v; asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(a)); return v; } };
+template <> struct LdsRaw<16> { typedef ulonglong2 V; static __device__ __forceinline__ V ld(uint32_t a) { ulonglong2 v; asm volatile("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "r"(a)); return v; } };
+template <class T> __device__ __forceinline__ T lds_elem(uint32_t a)
 {
-    const T *x = (const T *)p.x;
-    int64_t src = 0;
-    bool init = false;
+    typename LdsRaw<sizeof(T)>::V raw = LdsRaw<sizeof(T)>::ld(a);
+    T r;
+    memcpy(&r, &raw, sizeof(T));
+    return r;
+}
+
+// the tap loop: NQ accumulators (outputs along axis 0) per thread, taps in the reference's order, un-fused multiply/add
+template <class T, int NQ>
+__device__ __forceinline__ void tap_loop(uint32_t tile_addr, const T *s_w, const int32_t *s_off, int ntap, int step0_bytes, T *acc)
+{
 #pragma unroll
-    for (int a = 2; a >= 0; a--) {
-        if (c[a] >= p.P[a]) return Elem<T>::zero();     // only the 16-byte rounding of the window can reach past the padded extent
-        const int32_t m = p.map[a][c[a]];
-        if (m >= 0) src += (int64_t)m * p.xstr[a];
-        else if (m == NDC_MAP_INIT) init = true;
-        else return *(const T *)(m == NDC_MAP_CONST_FRONT ? p.cfront[a] : p.cback[a]);
+    for (int q = 0; q < NQ; q++) acc[q] = Elem<T>::zero();
+#pragma unroll 4
+    for (int t = 0; t < ntap; t++) {
+        const T w = s_w[t];
+        uint32_t a = tile_addr + (uint32_t)s_off[t];
+#pragma unroll
+        for (int q = 0; q < NQ; q++) { acc[q] = Elem<T>::mac(acc[q], lds_elem<T>(a), w); a += (uint32_t)step0_bytes; }
     }
-    return init ? Elem<T>::zero() : x[src];
 }
 
 template <class T>
@@ -97,42 +114,49 @@ __global__ void __launch_bounds__(kThreads) direct_tile_kernel(const __grid_cons
     const int nrows = p.IT[0] * p.IT[1];
     const int64_t c2_lo = c_lo[2] - shift2;
 
-    // value of the padded array along one tile row for i2 in [lo, hi): the two outer axes are resolved once per row
-    // (highest-numbered constant axis wins, never-written cells read 0), lanes sweep the contiguous axis
-    auto fill_row = [&](int row, int lo, int hi, int lo2, int hi2) {      // fills [lo,hi) and [lo2,hi2) of the row
-        const T *x = (const T *)p.x;
-        const int i0 = row / p.IT[1], i1 = row - i0 * p.IT[1];
-        const int64_t c0 = c_lo[0] + i0, c1 = c_lo[1] + i1;
-        T *trow = tile + row * row_elems;
-        bool zero = c0 >= p.P[0] || c1 >= p.P[1], has_const = false;
-        const unsigned char *cval = nullptr;
-        int64_t base = 0;
-        if (!zero) {
-            const int32_t m1 = p.map[1][c1];
-            if (m1 >= 0) base += (int64_t)m1 * p.xstr[1];
-            else if (m1 == NDC_MAP_INIT) zero = true;
-            else { has_const = true; cval = (m1 == NDC_MAP_CONST_FRONT) ? p.cfront[1] : p.cback[1]; }
-            if (!has_const) {
-                const int32_t m0 = p.map[0][c0];
-                if (m0 >= 0) base += (int64_t)m0 * p.xstr[0];
-                else if (m0 == NDC_MAP_INIT) zero = true;
-                else { has_const = true; cval = (m0 == NDC_MAP_CONST_FRONT) ? p.cfront[0] : p.cback[0]; }
+    // window maps in shared memory: s_map[a][i] = border map of padded coordinate c_lo[a] + i (kBeyond outside [0, P[a]))
+    constexpr int32_t kBeyond = INT32_MIN;
+    int32_t *s_map0 = s_off + p.ntap, *s_map1 = s_map0 + p.IT[0], *s_map2 = s_map1 + p.IT[1];
+    for (int e = tid; e < p.IT[0] + p.IT[1] + row_elems; e += kThreads) {
+        const int a = e < p.IT[0] ? 0 : (e < p.IT[0] + p.IT[1] ? 1 : 2);
+        const int i = e - (a == 0 ? 0 : (a == 1 ? p.IT[0] : p.IT[0] + p.IT[1]));
+        const int64_t c = (a == 2 ? c2_lo : c_lo[a]) + i;
+        s_map0[e] = (c < 0 || c >= p.P[a]) ? kBeyond : p.map[a][c];
+    }
+    // value of the padded array at window element (i0, i1, i2): the highest-numbered constant axis wins, never-written cells
+    // and the 16-byte rounding slack read 0 (same precedence as the sequential padding of src/padding/mod.rs:119-153)
+    auto resolve = [&](int i0, int i1, int i2) -> T {
+        const int32_t m2 = s_map2[i2], m1 = s_map1[i1], m0 = s_map0[i0];
+        if (m2 == kBeyond || m1 == kBeyond || m0 == kBeyond) return Elem<T>::zero();
+        if (m2 == NDC_MAP_CONST_FRONT) return *(const T *)p.cfront[2];
+        if (m2 == NDC_MAP_CONST_BACK) return *(const T *)p.cback[2];
+        if (m1 == NDC_MAP_CONST_FRONT) return *(const T *)p.cfront[1];
+        if (m1 == NDC_MAP_CONST_BACK) return *(const T *)p.cback[1];
+        if (m0 == NDC_MAP_CONST_FRONT) return *(const T *)p.cfront[0];
+        if (m0 == NDC_MAP_CONST_BACK) return *(const T *)p.cback[0];
+        if (m2 == NDC_MAP_INIT || m1 == NDC_MAP_INIT || m0 == NDC_MAP_INIT) return Elem<T>::zero();
+        return ((const T *)p.x)[(int64_t)m0 * p.xstr[0] + (int64_t)m1 * p.xstr[1] + (int64_t)m2 * p.xstr[2]];
+    };
+    // fill `nq * width` window rows, row (q, j) -> (i0, i1) by `rowmap`, elements h in [0, nsel) -> i2 by `colmap`.  The whole CTA
+    // works on it, `rows_it` rows per iteration, one element per thread and iteration, so the gathers of an iteration are
+    // independent loads (a warp per row with a map lookup feeding each load serialised ~20 us of latency on edge tiles of c4)
+    auto fill_rows = [&](int nq, int width, int nsel, auto rowmap, auto colmap) {
+        if (nq <= 0 || width <= 0 || nsel <= 0) return;
+        int lanes = 1;
+        while (lanes < nsel && lanes < kThreads) lanes <<= 1;
+        const int rows_it = kThreads / lanes, sub = tid / lanes, ln = tid - sub * lanes;
+        const int total = nq * width;
+        int q = sub / width, j = sub - q * width;
+#pragma unroll 4
+        for (int r = sub; r < total; r += rows_it) {
+            int i0, i1;
+            rowmap(q, j, i0, i1);
+            for (int h = ln; h < nsel; h += lanes) {
+                const int i2 = colmap(h);
+                tile[(i0 * p.IT[1] + i1) * row_elems + i2] = resolve(i0, i1, i2);
             }
-        }
-        const int n1 = hi - lo, ntot = n1 + (hi2 - lo2);
-#pragma unroll 2
-        for (int e = lane; e < ntot; e += 32) {
-            const int i2 = e < n1 ? lo + e : lo2 + (e - n1);
-            const int64_t c2 = c2_lo + i2;
-            T val = Elem<T>::zero();
-            if (c2 >= 0 && c2 < p.P[2] && !(c0 >= p.P[0] || c1 >= p.P[1])) {
-                const int32_t m2 = p.map[2][c2];
-                if (m2 == NDC_MAP_CONST_FRONT) val = *(const T *)p.cfront[2];
-                else if (m2 == NDC_MAP_CONST_BACK) val = *(const T *)p.cback[2];
-                else if (has_const) val = *(const T *)cval;
-                else if (m2 != NDC_MAP_INIT && !zero) val = x[base + (int64_t)m2 * p.xstr[2]];
-            }
-            trow[i2] = val;
+            j += rows_it;
+            while (j >= width) { j -= width; q++; }
         }
     };
 
@@ -150,21 +174,24 @@ __global__ void __launch_bounds__(kThreads) direct_tile_kernel(const __grid_cons
                 ::"r"(smem_u32(tile)), "l"(reinterpret_cast<uint64_t>(&tmap)), "r"(cx2), "r"(cx1), "r"(cx0), "r"(mb)
                 : "memory");
         }
-    } else {
-        for (int row = warp; row < nrows; row += kThreads / 32) fill_row(row, 0, row_elems, 0, 0);
     }
-    // taps -> shared memory: (offset inside the tile, weight), reference order
+    // taps -> shared memory: (byte offset inside the tile, weight), reference order
     for (int t = tid; t < p.ntap; t += kThreads) {
         const int32_t *o = p.tap_off + t * NDC_MAX_DIM;
         int off = 0;
         if (p.axis_shift <= 0) off += o[0 - p.axis_shift] * plane_elems;
         if (p.axis_shift <= 1) off += o[1 - p.axis_shift] * row_elems;
         off += o[2 - p.axis_shift];
-        s_off[t] = off;
+        s_off[t] = off * (int)sizeof(T);           // byte offset inside the tile
         s_w[t] = ((const T *)p.tap_w)[t];
     }
     __syncthreads();
-    if (tma_ok) {
+    auto ident_col = [&](int h) { return h; };
+    if (!tma_ok) {
+        // no TMA (1/2/16-byte elements, unaligned rows, strided views): gather the whole window through the maps
+        fill_rows(p.IT[0], p.IT[1], row_elems, [&](int q, int j, int &i0, int &i1) { i0 = q; i1 = j; }, ident_col);
+        __syncthreads();
+    } else {
         const uint32_t mb = smem_u32(&mbar);
         uint32_t done = 0;
         while (!done) {
@@ -175,26 +202,19 @@ __global__ void __launch_bounds__(kThreads) direct_tile_kernel(const __grid_cons
                 : "=r"(done) : "r"(mb), "r"(0u) : "memory");
         }
         if (need_patch) {
-            // halo patch.  (1) fringes: rows inside the array on the outer axes only leave it along axis 2 -- one thread per
-            // (row, fringe element), so the per-row map lookups run 32 rows at a time; (2) rows that lie outside the array on
-            // an outer axis are rebuilt whole, one warp per row.
+            // halo patch: only the window elements that fall outside the array are rebuilt through the maps.  Rows
+            // [lo0, hi0) x [lo1, hi1) lie inside the array on the outer axes and only need their axis-2 fringes [0, f2) and
+            // [b2, row_elems); the rows above (i0 < lo0), below (i0 >= hi0) and beside them (i1 outside [lo1, hi1)) are rebuilt whole.
+            const int lo0 = (int)min((int64_t)p.IT[0], max((int64_t)0, p.pf[0] - c_lo[0])), hi0 = (int)max((int64_t)lo0, min((int64_t)p.IT[0], p.pf[0] + p.n[0] - c_lo[0]));
+            const int lo1 = (int)min((int64_t)p.IT[1], max((int64_t)0, p.pf[1] - c_lo[1])), hi1 = (int)max((int64_t)lo1, min((int64_t)p.IT[1], p.pf[1] + p.n[1] - c_lo[1]));
             const int f2 = (int)min((int64_t)row_elems, max((int64_t)0, p.pf[2] - c2_lo));                 // [0, f2) is front halo
-            const int b2 = (int)min((int64_t)row_elems, max((int64_t)0, p.pf[2] + p.n[2] - c2_lo));       // [b2, row_elems) is back halo
-            const int nh = f2 + (row_elems - b2);
-            for (int e = tid; e < nrows * nh; e += kThreads) {
-                const int row = e / nh, h = e - row * nh;
-                const int i2 = h < f2 ? h : b2 + (h - f2);
-                const int i0 = row / p.IT[1], i1 = row - i0 * p.IT[1];
-                const int64_t c[3] = {c_lo[0] + i0, c_lo[1] + i1, c2_lo + i2};
-                const bool outer = c[0] < p.pf[0] || c[0] >= p.pf[0] + p.n[0] || c[1] < p.pf[1] || c[1] >= p.pf[1] + p.n[1];
-                if (!outer) tile[row * row_elems + i2] = c[2] < 0 ? Elem<T>::zero() : tile_padded_at<T>(p, c);
-            }
-            for (int row = warp; row < nrows; row += kThreads / 32) {
-                const int i0 = row / p.IT[1], i1 = row - i0 * p.IT[1];
-                const int64_t c0 = c_lo[0] + i0, c1 = c_lo[1] + i1;
-                const bool outer = c0 < p.pf[0] || c0 >= p.pf[0] + p.n[0] || c1 < p.pf[1] || c1 >= p.pf[1] + p.n[1];
-                if (outer) fill_row(row, 0, row_elems, 0, 0);
-            }
+            const int b2 = (int)max((int64_t)f2, min((int64_t)row_elems, max((int64_t)0, p.pf[2] + p.n[2] - c2_lo)));       // [b2, row_elems) is back halo
+            const int wside = lo1 + (p.IT[1] - hi1);
+            fill_rows(lo0, p.IT[1], row_elems, [&](int q, int j, int &i0, int &i1) { i0 = q; i1 = j; }, ident_col);
+            fill_rows(p.IT[0] - hi0, p.IT[1], row_elems, [&](int q, int j, int &i0, int &i1) { i0 = hi0 + q; i1 = j; }, ident_col);
+            fill_rows(hi0 - lo0, wside, row_elems, [&](int q, int j, int &i0, int &i1) { i0 = lo0 + q; i1 = j < lo1 ? j : hi1 + (j - lo1); }, ident_col);
+            fill_rows(hi0 - lo0, hi1 - lo1, f2 + (row_elems - b2), [&](int q, int j, int &i0, int &i1) { i0 = lo0 + q; i1 = lo1 + j; },
+                      [&](int h) { return h < f2 ? h : b2 + (h - f2); });
             __syncthreads();
         }
     }
@@ -203,16 +223,14 @@ __global__ void __launch_bounds__(kThreads) direct_tile_kernel(const __grid_cons
     if (o1l < p.TO[1]) {
         const int64_t o1 = (int64_t)t1 * p.TO[1] + o1l, o2 = (int64_t)t2 * p.TO[2] + o2l;
         T acc[kMaxTO0];
-#pragma unroll
-        for (int q = 0; q < kMaxTO0; q++) acc[q] = Elem<T>::zero();
         const int base = o1l * (int)p.s[1] * row_elems + o2l * (int)p.s[2] + shift2;
-        const int step0 = (int)p.s[0] * plane_elems;
-        for (int t = 0; t < p.ntap; t++) {
-            const T w = s_w[t];
-            const int off = base + s_off[t];
-#pragma unroll
-            for (int q = 0; q < kMaxTO0; q++)
-                if (q < p.TO[0]) acc[q] = Elem<T>::mac(acc[q], tile[off + q * step0], w);
+        const uint32_t tile_addr = smem_u32(tile) + (uint32_t)base * (uint32_t)sizeof(T);
+        const int step0_bytes = (int)p.s[0] * plane_elems * (int)sizeof(T);
+        switch (p.TO[0]) {
+        case 1: tap_loop<T, 1>(tile_addr, s_w, s_off, p.ntap, step0_bytes, acc); break;
+        case 2: tap_loop<T, 2>(tile_addr, s_w, s_off, p.ntap, step0_bytes, acc); break;
+        case 3: tap_loop<T, 3>(tile_addr, s_w, s_off, p.ntap, step0_bytes, acc); break;
+        default: tap_loop<T, 4>(tile_addr, s_w, s_off, p.ntap, step0_bytes, acc); break;
         }
         if (o1 < p.O[1] && o2 < p.O[2]) {
             T *out = (T *)p.out;
