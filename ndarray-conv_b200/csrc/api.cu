@@ -398,7 +398,7 @@ static int make_plan(const Geom &g, FftPlan *pl)
         }
         int st = plan_axis(g.P[a], g.Kd[a], cap, real_axis, &pl->tl[a]); if (st) return st;
         int L = real_axis ? pl->tl[a].F / 2 : pl->tl[a].F;
-        if (!factor_radices(L, &pl->fl[a])) { set_error("internal: non-smooth FFT length"); return NDCONV_ERR_INTERNAL; }
+        if (!factor_radices(L, &pl->fl[a], is_dbl ? 16 : 32)) { set_error("internal: non-smooth FFT length"); return NDCONV_ERR_INTERNAL; }
     }
     const int Fl = pl->tl[N - 1].F;
     pl->H = is_cx ? Fl : Fl / 2 + 1;
@@ -1264,7 +1264,7 @@ static int fft_nd_t(ndconv_processor *p, bool is_cx, int N, const int64_t *shape
         const int cap = last ? cap_last_axis(is_cx, is_dbl) : cap_col_axis(is_dbl);
         if (shape[a] > cap || (real_axis && (shape[a] & 1))) { set_error("fft: axis length outside this build's envelope (<= one shared-memory transform, even real axis)"); return NDCONV_ERR_UNSUPPORTED; }
         pl.tl[a].F = (int)shape[a]; pl.tl[a].V = (int)shape[a]; pl.tl[a].ntiles = 1;
-        if (!factor_radices(real_axis ? (int)shape[a] / 2 : (int)shape[a], &pl.fl[a])) { set_error("fft: length is not {2,3,5,7}-smooth (Bluestein not implemented)"); return NDCONV_ERR_UNSUPPORTED; }
+        if (!factor_radices(real_axis ? (int)shape[a] / 2 : (int)shape[a], &pl.fl[a], is_dbl ? 16 : 32)) { set_error("fft: length is not {2,3,5,7}-smooth (Bluestein not implemented)"); return NDCONV_ERR_UNSUPPORTED; }
     }
     const int Fl = pl.tl[N - 1].F;
     pl.H = is_cx ? Fl : Fl / 2 + 1;

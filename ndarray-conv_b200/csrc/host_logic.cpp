@@ -189,14 +189,15 @@ void build_taps(const Geom &g, const void *kernel, Taps &t)
 }
 
 // ---- FFT planning --------------------------------------------------------------------------------
-bool factor_radices(int L, FftLen *out)
+bool factor_radices(int L, FftLen *out, int max_radix)
 {
     if (L < 1) return false;
     FftLen f; f.L = L; f.npass = 0;
     int r = L;
     // large power-of-two radices first, then odd primes
-    // greedy: as few passes as possible (each pass is one shared-memory round trip)
-    while (r % 32 == 0 && r != 64 && r != 128 && r != 256 && f.npass < NDC_MAX_PASS) { f.radix[f.npass++] = 32; r /= 32; }
+    // greedy: as few passes as possible (each pass is one shared-memory round trip).  max_radix = 16 for f64: a radix-32
+    // butterfly of doubles needs 128 registers for its data alone and spills
+    while (max_radix >= 32 && r % 32 == 0 && r != 64 && r != 128 && r != 256 && f.npass < NDC_MAX_PASS) { f.radix[f.npass++] = 32; r /= 32; }
     while (r % 16 == 0 && r != 32 && r != 64 && f.npass < NDC_MAX_PASS) { f.radix[f.npass++] = 16; r /= 16; }
     while (r % 8 == 0 && f.npass < NDC_MAX_PASS) { f.radix[f.npass++] = 8; r /= 8; }
     while (r % 4 == 0 && f.npass < NDC_MAX_PASS) { f.radix[f.npass++] = 4; r /= 4; }

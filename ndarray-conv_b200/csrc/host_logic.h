@@ -56,7 +56,7 @@ struct FftLen {
     int L = 0, npass = 0;
     int radix[NDC_MAX_PASS];
 };
-bool factor_radices(int L, FftLen *out);          // false unless L is {2,3,5,7}-smooth
+bool factor_radices(int L, FftLen *out, int max_radix = 32);          // false unless L is {2,3,5,7}-smooth
 int64_t smooth_ge(int64_t n, bool even);
 double fft_len_cost(int F, bool real_axis);
 

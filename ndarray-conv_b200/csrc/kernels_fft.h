@@ -195,7 +195,7 @@ HD cx<R> *fft_smem(const BlockCtx &c, cx<R> *a, cx<R> *b, const FftPlanDev<R> &p
         case 5: stockham_pass_r<R, 5>(c, in, out, pl.L, Ns, tw, inv, nbatch, estride, bstride, batch_fast, pl.by_m[p], pl.by_ns[p]); break;
         case 7: stockham_pass_r<R, 7>(c, in, out, pl.L, Ns, tw, inv, nbatch, estride, bstride, batch_fast, pl.by_m[p], pl.by_ns[p]); break;
         case 16: stockham_pass_r<R, 16>(c, in, out, pl.L, Ns, tw, inv, nbatch, estride, bstride, batch_fast, pl.by_m[p], pl.by_ns[p]); break;
-        case 32: stockham_pass_r<R, 32>(c, in, out, pl.L, Ns, tw, inv, nbatch, estride, bstride, batch_fast, pl.by_m[p], pl.by_ns[p]); break;
+        case 32: if constexpr (sizeof(R) == 4) stockham_pass_r<R, 32>(c, in, out, pl.L, Ns, tw, inv, nbatch, estride, bstride, batch_fast, pl.by_m[p], pl.by_ns[p]); break;   // f64 plans stop at radix 16 (factor_radices)
         default: stockham_pass_r<R, 8>(c, in, out, pl.L, Ns, tw, inv, nbatch, estride, bstride, batch_fast, pl.by_m[p], pl.by_ns[p]); break;
         }
         Ns *= r;
