@@ -332,6 +332,8 @@ def other_shapes(pkg, lib, proc, dev, stream):
         ("c3 3D Complex<f32> x=(10,100,200) k=(5,11,31) Same Zeros", "fft", np.complex64, (10, 100, 200), (5, 11, 31), 1, pkg.ConvMode.Same, pkg.PaddingMode.Zeros),
         ("c4 3D direct conv i32 x=(64,256,256) k=(3,5,5) pad(1,2,2) stride 2 Replicate", "direct", np.int32, (64, 256, 256), (3, 5, 5), 1,
          pkg.ConvMode.Custom([1, 2, 2], [2, 2, 2]), pkg.PaddingMode.Replicate),
+        # not a BASELINE config: a large 1-D problem, where the rank-1 kernel is a single pass over memory (8 B per sample)
+        ("extra 1D f32 x=67108864 k=63 Full Reflect", "fft", np.float32, (1 << 26,), (63,), 1, pkg.ConvMode.Full, pkg.PaddingMode.Reflect),
     ]
     out = []
     for ci, (name, path, dt, xs, ks, dil, mode, pm) in enumerate(cfgs):
@@ -375,6 +377,7 @@ def other_shapes(pkg, lib, proc, dev, stream):
         kp = read_profile(lib, proc)
         lib.c.ndconv_processor_set_profiling(proc.handle, 0)
         out.append({"shape": name, "us_per_call": us, "Gsamples_per_s": n_out / us / 1e3, "launches_per_call": nl,
+                    "compulsory_GBps": (xh.nbytes + kh.nbytes + n_out * xh.itemsize) / us / 1e3,
                     "kernel_us_per_call": {k["kernel"]: round(k["total_ms"] * 1e3 / 10, 2) for k in kp},
                     "note": "device-resident, warm processor, includes host-side planning of every call"})
     return out

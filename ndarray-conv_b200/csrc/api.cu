@@ -340,12 +340,12 @@ static bool fast_eligible(const Geom &g)
 {
 #ifdef NDCONV_CUDA
     static const bool disabled = getenv("NDCONV_DISABLE_OPT") != nullptr;
-    if (disabled || g.dtype != NDCONV_F32 || (g.ndim != 2 && g.ndim != 3)) return false;
+    if (disabled || g.dtype != NDCONV_F32 || g.ndim < 1 || g.ndim > 3) return false;
     const int al = g.ndim - 1;
     if (g.P[al] < 128 || g.Kd[al] > 1024) return false;
     int64_t tot = 1;
     for (int a = 0; a < g.ndim; a++) { tot *= g.P[a]; if (a < al && g.Kd[a] > 512) return false; }
-    if (tot < 16384) return false;
+    if (tot < (g.ndim == 1 ? 512 : 16384)) return false;
     // the row kernels decode work indices in 32 bits: rows (tile overlap inflates by < 2x per axis) x last-axis tiles must fit
     double work = (double)(g.P[al] / 128 + 2);
     for (int a = 0; a < al; a++) work *= 2.0 * (double)g.P[a] + 16.0;
@@ -438,7 +438,7 @@ static void plan_axis0_split(const ndconv_problem *pr, const Geom &g, const FftP
     e->split_out = 0;
 #ifdef NDCONV_CUDA
     static const bool disabled = getenv("NDCONV_DISABLE_SPLIT") != nullptr;
-    if (disabled || !pl.fast) return;
+    if (disabled || !pl.fast || g.ndim < 2) return;
     const AxisTiling &t = pl.tl[0];
     if (t.ntiles < 2) return;
     if ((g.bf[0] == NDCONV_BORDER_CIRCULAR && g.pf[0] > 0) || (g.bb[0] == NDCONV_BORDER_CIRCULAR && g.pb[0] > 0)) return;
@@ -910,6 +910,12 @@ template <int T, int N> static void launch_row_n(bool inverse, const fast::RowPa
     if (inverse) fast::row_inv<T, N><<<grid, 128, fast::RowCfg<T>::smem, stm>>>(rp);
     else fast::row_fwd<T, N><<<grid, 128, fast::RowCfg<T>::smem, stm>>>(rp);
 }
+template <int T> static void launch_row1d(const fast::RowParams &rp, int grid, stream_t stm)
+{
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(fast::row1d<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, fast::Row1dCfg<T>::smem); attr = true; }
+    fast::row1d<T><<<grid, 128, fast::Row1dCfg<T>::smem, stm>>>(rp);
+}
 template <int T> static void launch_row(bool inverse, const fast::RowParams &rp, int grid, stream_t stm)
 {
     if (rp.ndim == 2) launch_row_n<T, 2>(inverse, rp, grid, stm);
@@ -952,7 +958,7 @@ static int conv_fft_fast(ndconv_processor *p, const ndconv_problem *pr, const Ge
         KfastParams kp; kp.kspec = (const cx<float> *)ent->buf.p; kp.kfast = (cx<float> *)ent->pair.p; kp.rows = rows_per_tile; kp.L = L; kp.Hp = pl.Hp;
         st = launch<KfastBody, KfastParams>(p->lc(), "kspec_fast_layout", (double)tile_elems * 16, p->num_sms * 4, 256, 0, kp); if (st) return st;
     }
-    st = p->ws.reserve((size_t)pl.ntiles_total * tile_elems * sizeof(cf)); if (st) return st;
+    if (N > 1) { st = p->ws.reserve((size_t)pl.ntiles_total * tile_elems * sizeof(cf)); if (st) return st; }
     const cx<float> *tw = nullptr, *twr = nullptr;
     st = get_tw_c<float>(p, L, &tw); if (st) return st;
     st = get_tw_r<float>(p, 2 * L, &twr); if (st) return st;
@@ -968,6 +974,21 @@ static int conv_fft_fast(ndconv_processor *p, const ndconv_problem *pr, const Ge
     }
     rp.x = (const float *)dev_x; rp.out = (float *)dev_out; rp.ws = (cf *)p->ws.p; rp.tw = tw; rp.twr = twr;
     rp.rows_per_tile = rows_per_tile; rp.tile_elems = tile_elems;
+    if (N == 1) {
+        // the whole pipeline in one launch and one pass over memory (fast::row1d): no workspace
+        rp.kfast = (const cf *)ent->pair.p; rp.nwork = pl.tl[0].ntiles;
+        const int64_t items = (rp.nwork + (32 / T) - 1) / (32 / T);
+        const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((items + 3) / 4, (int64_t)p->num_sms * 3 * 8));
+        const stream_t stm1 = p->stream;
+        return launch_raw(p->lc(), "row1d_fwd_mul_inv", 4.0 * (double)g.data_total + 4.0 * (double)g.out_total, [&] {
+            switch (T) {
+            case 32: launch_row1d<32>(rp, grid, stm1); break;
+            case 16: launch_row1d<16>(rp, grid, stm1); break;
+            case 8: launch_row1d<8>(rp, grid, stm1); break;
+            default: launch_row1d<4>(rp, grid, stm1); break;
+            }
+        });
+    }
 
     const double csz = 8.0;
     double S = (double)(g.P[al] / 2 + 1), So = S;           // un-inflated half spectrum of the padded array

@@ -64,7 +64,8 @@ struct RowParams {
     cf *ws;
     const cf *tw;                              // exp(-2 pi i j / L), j < L
     const cf *twr;                             // exp(-2 pi i k / 2L), k <= L/2
-    int64_t nwork;                             // rows to transform (fwd) / (output row, tile) pairs (inv)
+    const cf *kfast;                           // rank 1 only: the kernel spectrum of one tile in the workspace row layout
+    int64_t nwork;                             // rows to transform (fwd) / (output row, tile) pairs (inv) / tiles (rank 1)
     int64_t rows_per_tile, tile_elems;         // prod of the outer F ; rows_per_tile * (L + 8)
 };
 
@@ -380,6 +381,196 @@ __global__ void __launch_bounds__(128, 4) row_inv(const __grid_constant__ RowPar
                     const uint32_t o = q / s1;
                     if (o * s1 != q) continue;
                     if (o < O1) p.out[cur.orow + o] = h ? pk::im(v[j]) : pk::re(v[j]);
+                }
+            }
+        }
+    }
+}
+
+// ---- rank 1: the whole pipeline in one pass over memory ------------------------------------------------------------------------
+// One lane group per overlap-save tile: border-mapped loads, forward transform, R2C post-processing, multiply by the kernel
+// spectrum, C2R pre-processing, inverse transform, crop + stride -- all in registers and one warp-private exchange buffer.  The
+// paired slot k = (X[k], X[L-k]) that row_fwd would store is exactly what row_inv loads on the same lane, so nothing is
+// exchanged between the two halves and there is no workspace: the kernel reads x once and writes the output once.
+template <int T> struct Row1dCfg {
+    static constexpr int L = 32 * T;
+    static constexpr int smem = (L + L + L / 2 + L / 2 + 4 * RowCfg<T>::wstride) * 8;     // W (forward order), W (inverse order), post / pre tables, exchange
+};
+
+template <int T>
+__global__ void __launch_bounds__(128, 3) row1d(const __grid_constant__ RowParams p)
+{
+    constexpr int L = RowCfg<T>::L, M = RowCfg<T>::M, G = RowCfg<T>::G;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    pc *s_twF = reinterpret_cast<pc *>(smem_raw);         // s_twF[k1 * T + t] = W_L^{t k1}
+    pc *s_twI = s_twF + L;                                // s_twI[i * 32 + k1] = W_L^{i k1}
+    pc *s_post = s_twI + L;                               // (-i/2) w^k
+    pc *s_pre = s_post + L / 2;                           // i conj(w^k)
+    pc *s_ex = s_pre + L / 2;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane / T, t = lane % T;
+    for (int idx = threadIdx.x; idx < L; idx += blockDim.x) {
+        s_twF[idx] = ld_pc(p.tw + (idx / T) * (idx % T));
+        s_twI[idx] = ld_pc(p.tw + (idx >> 5) * (idx & 31));
+    }
+    for (int idx = threadIdx.x; idx < L / 2; idx += blockDim.x) {
+        const cf w = p.twr[idx];
+        s_post[idx] = pk::mk(0.5f * w.im, -0.5f * w.re);
+        s_pre[idx] = pk::mk(w.im, w.re);
+    }
+    __syncthreads();
+    pc *sb = s_ex + warp * RowCfg<T>::wstride + g * RowCfg<T>::gstride;
+    const int src_lane = g * T + ((T - t) % T);
+    const pc half = pk::mk(0.5f, 0.5f);
+    const ulonglong2 *k4 = reinterpret_cast<const ulonglong2 *>(p.kfast);
+    const int64_t nwarp_items = (p.nwork + G - 1) / G;
+    for (int64_t wi = (int64_t)blockIdx.x * 4 + warp; wi < nwarp_items; wi += (int64_t)gridDim.x * 4) {
+        const int64_t tl = wi * G + g;
+        const bool active = tl < p.nwork;
+        const int64_t cl0 = tl * p.V[0];
+        pc v[32];
+        // ---- load: padded samples [cl0, cl0 + 2L) ----
+        const bool interior = active && p.xstr[0] == 1 && cl0 >= p.pf[0] && cl0 + 2 * L <= p.pf[0] + p.n[0];
+        if (interior) {
+            const float *src = p.x + (cl0 - p.pf[0]);
+            if ((reinterpret_cast<uintptr_t>(src) & 7) == 0) {
+                const unsigned long long *s2 = reinterpret_cast<const unsigned long long *>(src);
+#pragma unroll
+                for (int j = 0; j < 32; j++) v[j].v = __ldg(s2 + t + T * j);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; j++) { const int e = 2 * (t + T * j); v[j] = pk::mk(__ldg(src + e), __ldg(src + e + 1)); }
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; j++) {
+                float q[2];
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const int64_t cl = cl0 + 2 * (t + T * j) + h;
+                    float val = 0.f;
+                    if (active && cl < p.P[0]) {
+                        const int64_t cc = cl - p.pf[0];
+                        if (cc >= 0 && cc < p.n[0]) val = __ldg(p.x + cc * p.xstr[0]);
+                        else {
+                            const int32_t m = p.map[0][cl];
+                            if (m == NDC_MAP_CONST_FRONT) val = p.cfront[0];
+                            else if (m == NDC_MAP_CONST_BACK) val = p.cback[0];
+                            else if (m != NDC_MAP_INIT) val = __ldg(p.x + (int64_t)m * p.xstr[0]);
+                        }
+                    }
+                    q[h] = val;
+                }
+                v[j] = pk::mk(q[0], q[1]);
+            }
+        }
+        // ---- forward: radix 32 over j, twiddle, exchange, radix T ----
+        pk::dft<false, 32>(v);
+#pragma unroll
+        for (int k1 = 0; k1 < 32; k1++) sb[k1 * (T + 1) + t] = pk::cmul(v[k1], s_twF[k1 * T + t]);
+        __syncwarp();
+#pragma unroll
+        for (int m = 0; m < M; m++)
+#pragma unroll
+            for (int i = 0; i < T; i++) v[m * T + i] = sb[(t + T * m) * (T + 1) + i];
+        __syncwarp();
+#pragma unroll
+        for (int m = 0; m < M; m++) pk::dft<false, T>(v + m * T);         // v[m*T + k2] = Z[k], k = t + T m + 32 k2
+        // ---- R2C post-processing, multiply by the kernel spectrum, C2R pre-processing: slot k = (X[k], X[L-k]) ----
+        pc b[16];
+        const float knyq = pk::re(ld_pc(p.kfast + L));                    // K[L] (real: the kernel is real)
+#pragma unroll
+        for (int m = 0; m < M; m++) {
+#pragma unroll
+            for (int k2 = 0; k2 < T / 2; k2++) {
+                const int ia = (M - 1 - m) * T + (T - 1 - k2);                                    // lanes t > 0
+                const int ib = ((M - m) % M) * T + (m > 0 ? T - 1 - k2 : (k2 > 0 ? T - k2 : T / 2)); // lane t == 0 (own registers)
+                float px = __shfl_sync(0xffffffffu, pk::re(v[ia]), src_lane);
+                float py = __shfl_sync(0xffffffffu, pk::im(v[ia]), src_lane);
+                if (t == 0) { px = pk::re(v[ib]); py = pk::im(v[ib]); }
+                const pc zk = v[m * T + k2];
+                const int k = t + T * m + 32 * k2;
+                const ulonglong2 kq = k4[k];                                                       // (K[k], K[L-k]) ; slot 0: (K[0], K[L/2])
+                pc ka, kb; ka.v = kq.x; kb.v = kq.y;
+                pc nzk, nzp;
+                if (k == 0) {
+                    const float x0 = pk::re(zk) + pk::im(zk), xl = pk::re(zk) - pk::im(zk);      // X[0], X[L]: real
+                    const float y0 = x0 * pk::re(ka), yl = xl * knyq;
+                    const pc ym = pk::cmul(pk::mk(px, -py), kb);                                   // Y[L/2] = conj Z[L/2] * K[L/2]
+                    nzk = pk::mk(y0 + yl, y0 - yl);                                                // Z'[0]
+                    nzp = pk::mk(2.f * pk::re(ym), -2.f * pk::im(ym));                             // Z'[L/2] = 2 conj Y[L/2]
+                } else {
+                    const pc cp = pk::mk(px, -py);
+                    const pc e2 = pk::add(zk, cp), d = pk::sub(zk, cp);
+                    const pc tw = pk::cmul(d, s_post[k]);
+                    const pc yk = pk::cmul(pk::fma(e2, half, tw), ka);                             // Y[k] = X[k] K[k]
+                    const pc ym = pk::cmul(pk::conj(pk::fma(e2, half, pk::neg(tw))), kb);          // Y[L-k] = X[L-k] K[L-k]
+                    const pc cm = pk::conj(ym);
+                    const pc E = pk::add(yk, cm), D = pk::sub(yk, cm);
+                    const pc O = pk::cmul(D, s_pre[k]);
+                    nzk = pk::add(E, O);
+                    nzp = pk::conj(pk::sub(E, O));
+                }
+                b[m * (T / 2) + k2] = nzp;
+                v[m * T + k2] = nzk;          // in place: partners are only ever read from the upper-half registers (k2 >= T/2)
+            }
+        }
+        // deliver Z'[L-k] to its owner: register (mr, k2r >= T/2) of lane t comes from lane (T-t)%T
+#pragma unroll
+        for (int mr = 0; mr < M; mr++) {
+#pragma unroll
+            for (int k2r = T / 2; k2r < T; k2r++) {
+                const int ia = (M - 1 - mr) * (T / 2) + (T - 1 - k2r);                                            // source lanes t' > 0
+                const int ib = mr > 0 ? (M - mr) * (T / 2) + (T - 1 - k2r) : (k2r == T / 2 ? 0 : (T - k2r));      // lane 0: own b[]
+                float px = __shfl_sync(0xffffffffu, pk::re(b[ia]), src_lane);
+                float py = __shfl_sync(0xffffffffu, pk::im(b[ia]), src_lane);
+                if (t == 0) { px = pk::re(b[ib]); py = pk::im(b[ib]); }
+                v[mr * T + k2r] = pk::mk(px, py);
+            }
+        }
+        // ---- inverse: radix T over k2, conj twiddle, exchange, radix 32 over k1 ----
+#pragma unroll
+        for (int m = 0; m < M; m++) pk::dft<true, T>(v + m * T);
+        __syncwarp();
+#pragma unroll
+        for (int m = 0; m < M; m++)
+#pragma unroll
+            for (int i = 0; i < T; i++) sb[(t + T * m) * (T + 1) + i] = pk::cmulc(v[m * T + i], s_twI[i * 32 + (t + T * m)]);
+        __syncwarp();
+#pragma unroll
+        for (int k1 = 0; k1 < 32; k1++) v[k1] = sb[k1 * (T + 1) + t];
+        __syncwarp();
+        pk::dft<true, 32>(v);                                            // v[j] = (y[2n], y[2n+1]), n = t + T j
+        if (!active) continue;
+        // ---- crop [Kd-1, 2L) of the tile, stride, store ----
+        const int Kd1 = p.Kd[0];
+        const int64_t mbase = tl * p.V[0];
+        if (p.s[0] == 1) {
+            const int64_t obase = mbase - (Kd1 - 1);
+            const bool vec_ok = (obase & 1) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 7) == 0;
+#pragma unroll
+            for (int j = 0; j < 32; j++) {
+                const int i = 2 * (t + T * j);
+                const int64_t o_lo = mbase + i - (Kd1 - 1);
+                const bool ok0 = i >= Kd1 - 1 && o_lo < p.O[0];
+                const bool ok1 = i + 1 >= Kd1 - 1 && o_lo + 1 < p.O[0];
+                if (vec_ok && ok0 && ok1) *reinterpret_cast<unsigned long long *>(p.out + o_lo) = v[j].v;
+                else {
+                    if (ok0) p.out[o_lo] = pk::re(v[j]);
+                    if (ok1) p.out[o_lo + 1] = pk::im(v[j]);
+                }
+            }
+        } else {
+            const int64_t s1 = p.s[0];
+#pragma unroll
+            for (int j = 0; j < 32; j++) {
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const int i = 2 * (t + T * j) + h;
+                    if (i < Kd1 - 1) continue;
+                    const int64_t q = mbase + i - (Kd1 - 1);
+                    const int64_t o = q / s1;
+                    if (o * s1 == q && o < p.O[0]) p.out[o] = h ? pk::im(v[j]) : pk::re(v[j]);
                 }
             }
         }

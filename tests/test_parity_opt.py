@@ -35,6 +35,14 @@ CASES = [
     ((1100, 4000), (5, 9), 2, "full", ("custom", [("const", 0.75), "circular"]), True),
     ((1100, 4000), (5, 9), 1, "same", ("custom", ["circular", "reflect"]), True),             # Circular on axis 0: never split
     ((600, 40, 300), (5, 3, 3), 1, "same", ("const", 0.25), True),                             # rank 3
+    # rank 1: fast::row1d, the whole pipeline in one launch (tiles of 256 .. 2048 samples)
+    ((5000,), (31,), 1, "same", "zeros", True),                                                # BASELINE configs[0]
+    ((700,), (5,), 1, "full", "reflect", True),
+    ((1000,), (100,), 1, "valid", "zeros", False),
+    ((3000,), (7,), 3, ("custom", [9], [2]), "replicate", True),
+    ((100000,), (63,), 1, "full", ("const", -1.5), True),
+    ((40000,), (33,), 2, "same", "circular", False),
+    ((65536,), (1000,), 1, ("explicit", [[17, 400]], [3]), ("explicit", [["reflect", "replicate"]]), True),
 ]
 
 
