@@ -340,9 +340,10 @@ static bool fast_eligible(const Geom &g)
 {
 #ifdef NDCONV_CUDA
     static const bool disabled = getenv("NDCONV_DISABLE_OPT") != nullptr;
-    if (disabled || g.dtype != NDCONV_F32 || g.ndim < 1 || g.ndim > 3) return false;
+    const bool cx32 = g.dtype == NDCONV_C32;
+    if (disabled || (g.dtype != NDCONV_F32 && !cx32) || g.ndim < (cx32 ? 2 : 1) || g.ndim > 3) return false;
     const int al = g.ndim - 1;
-    if (g.P[al] < 128 || g.Kd[al] > 1024) return false;
+    if (g.P[al] < (cx32 ? 64 : 128) || g.Kd[al] > (cx32 ? 512 : 1024)) return false;
     int64_t tot = 1;
     for (int a = 0; a < g.ndim; a++) { tot *= g.P[a]; if (a < al && g.Kd[a] > 512) return false; }
     if (tot < (g.ndim == 1 ? 512 : 16384)) return false;
@@ -379,12 +380,12 @@ static int make_plan(const Geom &g, FftPlan *pl)
     pl->fast = fast_eligible(g);
     for (int a = 0; a < N; a++) {
         if (pl->fast) {
-            static const int menu_last[4] = {256, 512, 1024, 2048}, menu_col[7] = {16, 32, 64, 128, 256, 512, 1024};
+            static const int menu_last[4] = {256, 512, 1024, 2048}, menu_last_cx[4] = {128, 256, 512, 1024}, menu_col[7] = {16, 32, 64, 128, 256, 512, 1024};
             pl->tl[a].F = 0;
-            if (a == N - 1) fast_pick_tile(g.P[a], g.Kd[a], menu_last, 4, &pl->tl[a]);
+            if (a == N - 1) fast_pick_tile(g.P[a], g.Kd[a], is_cx ? menu_last_cx : menu_last, 4, &pl->tl[a]);
             else fast_pick_tile(g.P[a], g.Kd[a], menu_col, 7, &pl->tl[a]);
             if (pl->tl[a].F == 0) { pl->fast = false; a = -1; continue; }      // no usable tile: replan everything on the generic path
-            if (!factor_radices(a == N - 1 ? pl->tl[a].F / 2 : pl->tl[a].F, &pl->fl[a])) return NDCONV_ERR_INTERNAL;
+            if (!factor_radices(a == N - 1 && !is_cx ? pl->tl[a].F / 2 : pl->tl[a].F, &pl->fl[a])) return NDCONV_ERR_INTERNAL;
             continue;
         }
         const bool last = (a == N - 1);
@@ -910,6 +911,22 @@ template <int T, int N> static void launch_row_n(bool inverse, const fast::RowPa
     if (inverse) fast::row_inv<T, N><<<grid, 128, fast::RowCfg<T>::smem, stm>>>(rp);
     else fast::row_fwd<T, N><<<grid, 128, fast::RowCfg<T>::smem, stm>>>(rp);
 }
+template <int T, int N> static void launch_row_cx_n(bool inverse, const fast::RowParams &rp, int grid, stream_t stm)
+{
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(fast::row_fwd_c<T, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, fast::RowCxCfg<T>::smem);
+        cudaFuncSetAttribute(fast::row_inv_c<T, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, fast::RowCxCfg<T>::smem);
+        attr = true;
+    }
+    if (inverse) fast::row_inv_c<T, N><<<grid, 128, fast::RowCxCfg<T>::smem, stm>>>(rp);
+    else fast::row_fwd_c<T, N><<<grid, 128, fast::RowCxCfg<T>::smem, stm>>>(rp);
+}
+template <int T> static void launch_row_cx(bool inverse, const fast::RowParams &rp, int grid, stream_t stm)
+{
+    if (rp.ndim == 2) launch_row_cx_n<T, 2>(inverse, rp, grid, stm);
+    else launch_row_cx_n<T, 3>(inverse, rp, grid, stm);
+}
 template <int T> static void launch_row1d(const fast::RowParams &rp, int grid, stream_t stm)
 {
     static bool attr = false;
@@ -948,20 +965,21 @@ static int conv_fft_fast(ndconv_processor *p, const ndconv_problem *pr, const Ge
 {
     using namespace ndc::fast;
     const int N = g.ndim, al = N - 1;
-    const int L = pl.tl[al].F / 2, pitch = L + kPad, T = L / 32;
+    const bool is_cx = pl.is_cx;                                 // Complex<f32>: C2C rows of L = F columns, no pairing, no pad columns
+    const int L = is_cx ? pl.tl[al].F : pl.tl[al].F / 2, pitch = is_cx ? L : L + kPad, T = L / 32;
     int st;
     int64_t rows_per_tile = 1;
     for (int a = 0; a < al; a++) rows_per_tile *= pl.tl[a].F;
     const int64_t tile_elems = rows_per_tile * pitch;
     if (!ent->pair.p) {
         st = ent->pair.reserve((size_t)tile_elems * sizeof(cf)); if (st) return st;
-        KfastParams kp; kp.kspec = (const cx<float> *)ent->buf.p; kp.kfast = (cx<float> *)ent->pair.p; kp.rows = rows_per_tile; kp.L = L; kp.Hp = pl.Hp;
+        KfastParams kp; kp.kspec = (const cx<float> *)ent->buf.p; kp.kfast = (cx<float> *)ent->pair.p; kp.rows = rows_per_tile; kp.L = L; kp.Hp = pl.Hp; kp.is_cx = is_cx ? 1 : 0;
         st = launch<KfastBody, KfastParams>(p->lc(), "kspec_fast_layout", (double)tile_elems * 16, p->num_sms * 4, 256, 0, kp); if (st) return st;
     }
     if (N > 1) { st = p->ws.reserve((size_t)pl.ntiles_total * tile_elems * sizeof(cf)); if (st) return st; }
     const cx<float> *tw = nullptr, *twr = nullptr;
     st = get_tw_c<float>(p, L, &tw); if (st) return st;
-    st = get_tw_r<float>(p, 2 * L, &twr); if (st) return st;
+    if (!is_cx) { st = get_tw_r<float>(p, 2 * L, &twr); if (st) return st; }
 
     fast::RowParams rp; memset(&rp, 0, sizeof(rp));
     rp.ndim = N;
@@ -971,6 +989,10 @@ static int conv_fft_fast(ndconv_processor *p, const ndconv_problem *pr, const Ge
         rp.F[a] = pl.tl[a].F; rp.V[a] = pl.tl[a].V; rp.ntiles[a] = pl.tl[a].ntiles; rp.Kd[a] = (int)g.Kd[a]; rp.s[a] = g.s[a]; rp.O[a] = g.O[a];
         rp.cfront[a] = pr->border[a][0].type == NDCONV_BORDER_CONST ? *(const float *)pr->border[a][0].value : 0.f;
         rp.cback[a] = pr->border[a][1].type == NDCONV_BORDER_CONST ? *(const float *)pr->border[a][1].value : 0.f;
+        if (is_cx) {
+            rp.cfront_im[a] = pr->border[a][0].type == NDCONV_BORDER_CONST ? ((const float *)pr->border[a][0].value)[1] : 0.f;
+            rp.cback_im[a] = pr->border[a][1].type == NDCONV_BORDER_CONST ? ((const float *)pr->border[a][1].value)[1] : 0.f;
+        }
     }
     rp.x = (const float *)dev_x; rp.out = (float *)dev_out; rp.ws = (cf *)p->ws.p; rp.tw = tw; rp.twr = twr;
     rp.rows_per_tile = rows_per_tile; rp.tile_elems = tile_elems;
@@ -991,13 +1013,22 @@ static int conv_fft_fast(ndconv_processor *p, const ndconv_problem *pr, const Ge
     }
 
     const double csz = 8.0;
-    double S = (double)(g.P[al] / 2 + 1), So = S;           // un-inflated half spectrum of the padded array
+    double S = is_cx ? (double)g.P[al] : (double)(g.P[al] / 2 + 1), So = S;           // un-inflated (half) spectrum of the padded array
     for (int a = 0; a < al; a++) { S *= (double)g.P[a]; So *= (double)g.O[a]; }
-    const double in_bytes = 4.0 * (double)g.data_total, out_bytes = 4.0 * (double)g.out_total;
+    const double in_bytes = (double)g.es * (double)g.data_total, out_bytes = (double)g.es * (double)g.out_total;
     const stream_t stm = p->stream;
     auto row_launch = [&](bool inverse) {
         const int64_t items = (rp.nwork + (32 / T) - 1) / (32 / T);
         const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((items + 3) / 4, (int64_t)p->num_sms * 4 * 8));
+        if (is_cx) {
+            switch (T) {
+            case 32: launch_row_cx<32>(inverse, rp, grid, stm); break;
+            case 16: launch_row_cx<16>(inverse, rp, grid, stm); break;
+            case 8: launch_row_cx<8>(inverse, rp, grid, stm); break;
+            default: launch_row_cx<4>(inverse, rp, grid, stm); break;
+            }
+            return;
+        }
         switch (T) {
         case 32: launch_row<32>(inverse, rp, grid, stm); break;
         case 16: launch_row<16>(inverse, rp, grid, stm); break;

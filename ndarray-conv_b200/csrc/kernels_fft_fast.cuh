@@ -57,6 +57,7 @@ struct RowParams {
     int64_t n[3], xstr[3], P[3], pf[3];
     const int32_t *map[3];
     float cfront[3], cback[3];
+    float cfront_im[3], cback_im[3];           // Complex<f32> problems: imaginary parts of the constant borders
     int F[3], V[3], ntiles[3], Kd[3];          // F[ndim-1] = 2L
     int64_t s[3], O[3];
     const float *x;
@@ -79,22 +80,22 @@ template <int T> struct RowCfg {
 
 struct RowSrcInfo {
     int64_t base, cl0;
-    float cval;
+    float cval, cval_im;
     bool zero, has_const, beyond, active;
     cf *dst;
 };
 
 // outer-axis resolution of one tile row: beyond the padded extent of an outer axis the FFT buffer is zero
 // (conv_fft/padding.rs:47-59); otherwise the highest-numbered constant axis wins and never-written cells read 0
-template <int N> __device__ __forceinline__ RowSrcInfo resolve_fwd_row(const RowParams &p, int64_t w, int L)
+template <int N> __device__ __forceinline__ RowSrcInfo resolve_fwd_row(const RowParams &p, int64_t w, int pitch)
 {
-    RowSrcInfo r; r.base = 0; r.cval = 0.f; r.zero = false; r.has_const = false; r.beyond = false; r.active = w < p.nwork; r.dst = nullptr; r.cl0 = 0;
+    RowSrcInfo r; r.base = 0; r.cval = 0.f; r.cval_im = 0.f; r.zero = false; r.has_const = false; r.beyond = false; r.active = w < p.nwork; r.dst = nullptr; r.cl0 = 0;
     if (!r.active) return r;
     // 32-bit index arithmetic (the host only takes this path when the work count fits; 64-bit division is ~5x dearer)
     const uint32_t w32 = (uint32_t)w, rpt = (uint32_t)p.rows_per_tile;
     const uint32_t tile = w32 / rpt;
     uint32_t row = w32 - tile * rpt;
-    r.dst = p.ws + (int64_t)tile * p.tile_elems + (int64_t)row * (L + kPad);
+    r.dst = p.ws + (int64_t)tile * p.tile_elems + (int64_t)row * pitch;
     uint32_t tt = tile;
     const uint32_t tl = tt % (uint32_t)p.ntiles[N - 1]; tt /= (uint32_t)p.ntiles[N - 1];
     r.cl0 = (int64_t)tl * p.V[N - 1];
@@ -113,7 +114,7 @@ template <int N> __device__ __forceinline__ RowSrcInfo resolve_fwd_row(const Row
         const int32_t m = p.map[a][c[a]];
         if (m >= 0) r.base += (int64_t)m * p.xstr[a];
         else if (m == NDC_MAP_INIT) r.zero = true;
-        else { r.has_const = true; r.cval = (m == NDC_MAP_CONST_FRONT) ? p.cfront[a] : p.cback[a]; }
+        else { r.has_const = true; r.cval = (m == NDC_MAP_CONST_FRONT) ? p.cfront[a] : p.cback[a]; r.cval_im = (m == NDC_MAP_CONST_FRONT) ? p.cfront_im[a] : p.cback_im[a]; }
     }
     return r;
 }
@@ -137,7 +138,7 @@ __global__ void __launch_bounds__(128, 4) row_fwd(const __grid_constant__ RowPar
     const pc half = pk::mk(0.5f, 0.5f);
     const int64_t nwarp_items = (p.nwork + G - 1) / G;
     for (int64_t wi = (int64_t)blockIdx.x * 4 + warp; wi < nwarp_items; wi += (int64_t)gridDim.x * 4) {
-        const RowSrcInfo ri = resolve_fwd_row<N>(p, wi * G + g, L);
+        const RowSrcInfo ri = resolve_fwd_row<N>(p, wi * G + g, L + kPad);
         if (__all_sync(0xffffffffu, !ri.active || ri.beyond)) {
             // rows beyond the padded extent of an outer axis: zero spectrum, no transform
             if (ri.active) {
@@ -234,7 +235,7 @@ struct RowInvInfo {
     int tl;
     bool active;
 };
-template <int N> __device__ __forceinline__ RowInvInfo resolve_inv_row(const RowParams &p, int64_t w, int L)
+template <int N> __device__ __forceinline__ RowInvInfo resolve_inv_row(const RowParams &p, int64_t w, int pitch)
 {
     RowInvInfo r; r.active = w < p.nwork; r.src = p.ws; r.orow = 0; r.tl = 0;
     if (!r.active) return r;
@@ -256,7 +257,7 @@ template <int N> __device__ __forceinline__ RowInvInfo resolve_inv_row(const Row
         obase = obase * p.O[a] + o[a];
     }
     tile = tile * ntl + r.tl;
-    r.src = p.ws + tile * p.tile_elems + row * (L + kPad);
+    r.src = p.ws + tile * p.tile_elems + row * pitch;
     r.orow = obase * p.O[N - 1];
     return r;
 }
@@ -282,7 +283,7 @@ __global__ void __launch_bounds__(128, 4) row_inv(const __grid_constant__ RowPar
     const int64_t wstep = (int64_t)gridDim.x * 4;
     int64_t wi = (int64_t)blockIdx.x * 4 + warp;
     if (wi >= nwarp_items) return;
-    RowInvInfo ri = resolve_inv_row<N>(p, wi * G + g, L);
+    RowInvInfo ri = resolve_inv_row<N>(p, wi * G + g, L + kPad);
     auto stage = [&](const RowInvInfo &r) {
         if (r.active) {
             const ulonglong2 *s4 = reinterpret_cast<const ulonglong2 *>(r.src);
@@ -348,7 +349,7 @@ __global__ void __launch_bounds__(128, 4) row_inv(const __grid_constant__ RowPar
         for (int k1 = 0; k1 < 32; k1++) v[k1] = sb[k1 * (T + 1) + t];
         __syncwarp();
         const RowInvInfo cur = ri;
-        if (wi + wstep < nwarp_items) { ri = resolve_inv_row<N>(p, (wi + wstep) * G + g, L); stage(ri); }
+        if (wi + wstep < nwarp_items) { ri = resolve_inv_row<N>(p, (wi + wstep) * G + g, L + kPad); stage(ri); }
         pk::dft<true, 32>(v);                                            // v[j] = z[t + T j] = (y[2n], y[2n+1]), n = t + T j
         if (!cur.active) continue;
         const int Kd1 = p.Kd[al];
@@ -383,6 +384,125 @@ __global__ void __launch_bounds__(128, 4) row_inv(const __grid_constant__ RowPar
                     if (o < O1) p.out[cur.orow + o] = h ? pk::im(v[j]) : pk::re(v[j]);
                 }
             }
+        }
+    }
+}
+
+// ---- Complex<f32> rows: C2C along the last axis (tiles of L = 32 T complex samples, workspace rows of exactly L columns) ----------
+// Same lane-group structure as row_fwd / row_inv without the real-transform algebra: the column kernels do not care what a column
+// holds, so rank 2 and 3 complex problems reuse col_pass unchanged (processor/complex.rs:33-145 in the reference).
+template <int T> struct RowCxCfg { static constexpr int L = 32 * T, smem = (L + 4 * RowCfg<T>::wstride) * 8; };
+
+template <int T, int N>
+__global__ void __launch_bounds__(128, 4) row_fwd_c(const __grid_constant__ RowParams p)
+{
+    constexpr int L = RowCfg<T>::L, M = RowCfg<T>::M, G = RowCfg<T>::G;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    pc *s_tw = reinterpret_cast<pc *>(smem_raw);          // s_tw[k1 * T + t] = W_L^{t k1}
+    pc *s_ex = s_tw + L;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane / T, t = lane % T;
+    for (int idx = threadIdx.x; idx < L; idx += blockDim.x) s_tw[idx] = ld_pc(p.tw + (idx / T) * (idx % T));
+    __syncthreads();
+    pc *sb = s_ex + warp * RowCfg<T>::wstride + g * RowCfg<T>::gstride;
+    constexpr int al = N - 1;
+    const cf *xc = reinterpret_cast<const cf *>(p.x);
+    const int64_t nwarp_items = (p.nwork + G - 1) / G;
+    for (int64_t wi = (int64_t)blockIdx.x * 4 + warp; wi < nwarp_items; wi += (int64_t)gridDim.x * 4) {
+        const RowSrcInfo ri = resolve_fwd_row<N>(p, wi * G + g, L);
+        if (__all_sync(0xffffffffu, !ri.active || ri.beyond)) {
+            if (ri.active) for (int q = t; q < L; q += T) st_pc(ri.dst + q, pk::mk(0.f, 0.f));
+            continue;
+        }
+        pc v[32];
+        const bool interior = ri.active && !ri.beyond && !ri.zero && !ri.has_const && p.xstr[al] == 1 && ri.cl0 >= p.pf[al] && ri.cl0 + L <= p.pf[al] + p.n[al];
+        if (interior) {
+            const cf *src = xc + ri.base + (ri.cl0 - p.pf[al]);
+#pragma unroll
+            for (int j = 0; j < 32; j++) v[j].v = __ldg(reinterpret_cast<const unsigned long long *>(src + t + T * j));
+        } else {
+            const bool plain = ri.active && !ri.beyond && !ri.zero && !ri.has_const;
+#pragma unroll
+            for (int j = 0; j < 32; j++) {
+                const int64_t cl = ri.cl0 + t + T * j;
+                pc val = pk::mk(0.f, 0.f);
+                const int64_t cc = cl - p.pf[al];
+                if (plain && cc >= 0 && cc < p.n[al]) val.v = __ldg(reinterpret_cast<const unsigned long long *>(xc + ri.base + cc * p.xstr[al]));
+                else if (ri.active && !ri.beyond && cl < p.P[al]) {
+                    const int32_t m = p.map[al][cl];
+                    if (m == NDC_MAP_CONST_FRONT) val = pk::mk(p.cfront[al], p.cfront_im[al]);
+                    else if (m == NDC_MAP_CONST_BACK) val = pk::mk(p.cback[al], p.cback_im[al]);
+                    else if (ri.has_const) val = pk::mk(ri.cval, ri.cval_im);
+                    else if (m != NDC_MAP_INIT && !ri.zero) val.v = __ldg(reinterpret_cast<const unsigned long long *>(xc + ri.base + (int64_t)m * p.xstr[al]));
+                }
+                v[j] = val;
+            }
+        }
+        pk::dft<false, 32>(v);
+#pragma unroll
+        for (int k1 = 0; k1 < 32; k1++) sb[k1 * (T + 1) + t] = pk::cmul(v[k1], s_tw[k1 * T + t]);
+        __syncwarp();
+#pragma unroll
+        for (int m = 0; m < M; m++)
+#pragma unroll
+            for (int i = 0; i < T; i++) v[m * T + i] = sb[(t + T * m) * (T + 1) + i];
+        __syncwarp();
+#pragma unroll
+        for (int m = 0; m < M; m++) pk::dft<false, T>(v + m * T);         // v[m*T + k2] = X[k], k = t + T m + 32 k2
+        if (ri.active) {
+#pragma unroll
+            for (int m = 0; m < M; m++)
+#pragma unroll
+                for (int k2 = 0; k2 < T; k2++) st_pc(ri.dst + t + T * m + 32 * k2, v[m * T + k2]);
+        }
+    }
+}
+
+template <int T, int N>
+__global__ void __launch_bounds__(128, 4) row_inv_c(const __grid_constant__ RowParams p)
+{
+    constexpr int L = RowCfg<T>::L, M = RowCfg<T>::M, G = RowCfg<T>::G;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    pc *s_tw = reinterpret_cast<pc *>(smem_raw);          // transposed: s_tw[i * 32 + k1] = W_L^{i k1}
+    pc *s_ex = s_tw + L;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane / T, t = lane % T;
+    for (int idx = threadIdx.x; idx < L; idx += blockDim.x) s_tw[idx] = ld_pc(p.tw + (idx >> 5) * (idx & 31));
+    __syncthreads();
+    pc *sb = s_ex + warp * RowCfg<T>::wstride + g * RowCfg<T>::gstride;
+    constexpr int al = N - 1;
+    cf *outc = reinterpret_cast<cf *>(p.out);
+    const int64_t nwarp_items = (p.nwork + G - 1) / G;
+    for (int64_t wi = (int64_t)blockIdx.x * 4 + warp; wi < nwarp_items; wi += (int64_t)gridDim.x * 4) {
+        const RowInvInfo ri = resolve_inv_row<N>(p, wi * G + g, L);
+        pc v[32];
+#pragma unroll
+        for (int m = 0; m < M; m++)
+#pragma unroll
+            for (int k2 = 0; k2 < T; k2++) v[m * T + k2] = ri.active ? ld_pc(ri.src + t + T * m + 32 * k2) : pk::mk(0.f, 0.f);
+#pragma unroll
+        for (int m = 0; m < M; m++) pk::dft<true, T>(v + m * T);
+#pragma unroll
+        for (int m = 0; m < M; m++)
+#pragma unroll
+            for (int i = 0; i < T; i++) sb[(t + T * m) * (T + 1) + i] = pk::cmulc(v[m * T + i], s_tw[i * 32 + (t + T * m)]);
+        __syncwarp();
+#pragma unroll
+        for (int k1 = 0; k1 < 32; k1++) v[k1] = sb[k1 * (T + 1) + t];
+        __syncwarp();
+        pk::dft<true, 32>(v);                                            // v[j] = y[t + T j]
+        if (!ri.active) continue;
+        const int Kd1 = p.Kd[al];
+        const int64_t mbase = (int64_t)ri.tl * p.V[al];
+        const uint32_t s1 = (uint32_t)(p.s[al] < 0x7fffffff ? p.s[al] : 0x7fffffff), O1 = (uint32_t)p.O[al];
+#pragma unroll
+        for (int j = 0; j < 32; j++) {
+            const int i = t + T * j;
+            if (i < Kd1 - 1) continue;
+            const uint32_t q = (uint32_t)(mbase + i - (Kd1 - 1));
+            const uint32_t o = s1 == 1 ? q : q / s1;
+            if (s1 != 1 && o * s1 != q) continue;
+            if (o < O1) st_pc(outc + ri.orow + o, v[j]);
         }
     }
 }
@@ -716,17 +836,19 @@ struct KfastParams {
     cx<float> *kfast;
     int64_t rows;
     int L, Hp;
+    int is_cx;        // Complex<f32> problems: rows of exactly L columns in natural bin order (no pairing)
 };
 struct KfastBody {
     static HD void run(const BlockCtx &c, const KfastParams &p)
     {
-        const int pitch = p.L + fast::kPad;
+        const int pitch = p.is_cx ? p.L : p.L + fast::kPad;
         const int64_t total = p.rows * pitch;
         for (int64_t e = c.bid * c.nt + c.tid; e < total; e += c.nb * c.nt) {
             const int64_t q = e / pitch;
             const int pc = (int)(e % pitch);
             cx<float> val = cx<float>{0.f, 0.f};
-            if (pc <= p.L) {
+            if (p.is_cx) val = p.kspec[q * p.Hp + pc];
+            else if (pc <= p.L) {
                 int bin;
                 if (pc == p.L) bin = p.L;
                 else if (pc == 0) bin = 0;

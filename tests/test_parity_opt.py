@@ -66,6 +66,38 @@ def test_opt2d_vs_oracle(pkg, cuda_lib, oracle, case):
     proc.close()
 
 
+CX_CASES = [
+    # Complex<f32>: C2C rows (fast::row_fwd_c / row_inv_c), last-axis tiles of 128 .. 1024 samples
+    ((10, 100, 200), (5, 11, 31), 1, "same", "zeros", True),                                 # BASELINE configs[2], Complex variant
+    ((300, 700), (5, 9), 1, "full", "reflect", True),
+    ((130, 2500), (4, 6), 2, "same", ("custom", ["circular", ("const", 1.5 - 0.75j)]), False),
+    ((1100, 1300), (7, 3), 1, ("custom", [3, 5], [2, 3]), "replicate", True),                 # strided; large enough for the axis-0 split
+    ((1025, 1030), (63, 63), 1, "valid", ("const", 0.25 + 2j), True),
+    ((40, 90, 130), (3, 4, 5), 1, "full", ("custom", ["reflect", ("const", -1j), "circular"]), False),
+    ((64, 64), (3, 3), 1, "same", "zeros", True),                                             # below the fast path's size threshold: generic kernels
+]
+
+
+@pytest.mark.parametrize("case", CX_CASES, ids=[str(c[:2]) for c in CX_CASES])
+def test_complex_fast_path_vs_oracle(pkg, cuda_lib, oracle, case):
+    shape, ks, dil, mode, padding, rev = case
+    rng = np.random.default_rng(7)
+    x = ((rng.random(shape) - 0.25) + 1j * (rng.random(shape) - 0.5)).astype(np.complex64)
+    k = ((rng.random(ks) - 0.5) + 1j * (rng.random(ks) - 0.25)).astype(np.complex64)
+    kw = pkg.with_dilation(k, dil)
+    if not rev:
+        kw = kw.no_reverse()
+    proc = pkg.get_fft_processor(0, cuda_lib)
+    got = pkg.conv_fft_with_processor(x, kw, mode_from_spec(pkg, mode), padding_from_spec(pkg, padding), proc)
+    got2 = pkg.conv_fft_with_processor(x, kw, mode_from_spec(pkg, mode), padding_from_spec(pkg, padding), proc)
+    ref = oracle.conv_f64_truth(x, k, mode, padding, dil, rev)
+    assert got.shape == ref.shape and got.dtype == np.complex64
+    tol = fft_tol(np.complex64, 1024 * 1024, ref, float(np.max(np.abs(x)) * np.sum(np.abs(k))))
+    assert np.max(np.abs(got - ref)) <= tol, (np.max(np.abs(got - ref)), tol)
+    assert np.array_equal(got, got2)
+    proc.close()
+
+
 def test_opt2d_matches_generic_path(pkg, cuda_lib):
     """same input through the fast path and (NDCONV_DISABLE_OPT=1, subprocess) the generic path"""
     import os
