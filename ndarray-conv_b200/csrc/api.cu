@@ -1281,8 +1281,27 @@ static int conv_fft_host_pipelined(ndconv_processor *p, const ndconv_problem *pr
 }
 #endif
 
+// A dilated kernel longer than the largest shared-memory FFT tile of its axis has no overlap-save tiling here (a two-level
+// transform would be needed).  The reference handles such kernels, so instead of refusing them the float / Complex problem is
+// evaluated by the direct kernel: exact tap-by-tap summation, O(outputs x taps) -- slow but inside the conv_fft tolerance.
+static bool kernel_exceeds_fft_tiles(const ndconv_problem *pr)
+{
+    if (!pr || pr->ndim < 1 || pr->ndim > NDC_MAX_DIM || !dtype_is_float(pr->dtype)) return false;
+    const bool is_cx = dtype_is_complex(pr->dtype), is_dbl = (pr->dtype == NDCONV_F64 || pr->dtype == NDCONV_C64);
+    for (int a = 0; a < pr->ndim; a++) {
+        if (pr->kernel_shape[a] < 1 || pr->dilation[a] < 1) return false;       // malformed: let the FFT path report it
+        const int64_t Kd = (pr->kernel_shape[a] - 1) * pr->dilation[a] + 1;
+        const int cap = a == pr->ndim - 1 ? cap_last_axis(is_cx, is_dbl) : cap_col_axis(is_dbl);
+        if (Kd > cap) return true;
+    }
+    return false;
+}
+
+static int conv_direct_impl(ndconv_processor *p, const ndconv_problem *pr, void *out);
+
 static int conv_fft_impl(ndconv_processor *p, const ndconv_problem *pr, void *out)
 {
+    if (kernel_exceeds_fft_tiles(pr)) return conv_direct_impl(p, pr, out);
 #ifdef NDCONV_CUDA
     if (pr && pr->memory == NDCONV_MEM_HOST) {
         Geom g; std::vector<int32_t> maps[NDC_MAX_DIM];

@@ -325,3 +325,24 @@ def test_tiled_overlap_save_paths(ndc, oracle):
     got = pkg.conv_fft(xc, kc, pkg.ConvMode.Same, pkg.PaddingMode.Replicate, lib=lib)
     ref = oracle.conv_f64_truth(xc, kc, "same", "replicate")
     assert np.max(np.abs(got - ref)) <= fft_tol(np.complex64, 32 * 4096, ref)
+
+
+def test_kernel_longer_than_an_fft_tile_is_evaluated_directly(ndc, oracle):
+    """A dilated kernel extent above the largest shared-memory FFT tile (8192 real points on the last axis, 1024 on the
+    others) has no overlap-save tiling; the reference handles such kernels, so conv_fft evaluates them with the direct
+    kernel instead of refusing them.  Tolerance: direct f32 summation of `taps` terms, c * eps * sqrt(taps) * max|out| bound."""
+    pkg, lib = ndc
+    rng = np.random.default_rng(21)
+    x = rng.standard_normal(12000).astype(np.float32)
+    k = rng.standard_normal(300).astype(np.float32)
+    got = pkg.conv_fft(x, pkg.with_dilation(k, 30), pkg.ConvMode.Same, pkg.PaddingMode.Reflect, lib=lib)      # Kd = 8971 > 8192
+    ref = oracle.conv_f64_truth(x, k, "same", "reflect", 30)
+    assert got.shape == ref.shape
+    tol = 4 * np.finfo(np.float32).eps * np.sqrt(300) * float(np.max(np.abs(x))) * float(np.sum(np.abs(k)))
+    assert np.max(np.abs(got - ref)) <= tol
+    x2 = rng.standard_normal((1500, 20)).astype(np.float32)
+    k2 = rng.standard_normal((40, 3)).astype(np.float32)
+    got = pkg.conv_fft(x2, pkg.with_dilation(k2, [27, 1]), pkg.ConvMode.Valid, pkg.PaddingMode.Zeros, lib=lib)  # Kd0 = 1054 > 1024
+    ref = oracle.conv_f64_truth(x2, k2, "valid", "zeros", [27, 1])
+    assert got.shape == ref.shape
+    assert np.max(np.abs(got - ref)) <= 4 * np.finfo(np.float32).eps * np.sqrt(120) * float(np.max(np.abs(x2))) * float(np.sum(np.abs(k2)))
