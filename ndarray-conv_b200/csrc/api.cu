@@ -170,6 +170,13 @@ struct ndconv_processor {
     // host-path slab pipeline (H2D | kernels | D2H overlapped)
     DevBuf pipe_in[2], pipe_out[2], pipe_row;
     DevBuf zero_map;             // one int32 0: identity border map of the dummy leading axes of the rank-3 tile kernel
+    // axis-0 split: the tail part runs on a second stream with a workspace of its own, beside the main part
+    DevBuf ws_aux;
+    stream_t aux_stream = nullptr;
+    bool in_split = false, on_aux = false;   // on_aux: the launches being issued belong to the tail part on the second stream
+#ifdef NDCONV_CUDA
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+#endif
     stream_t h2d_stream = nullptr, d2h_stream = nullptr;
 #ifdef NDCONV_CUDA
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
@@ -426,6 +433,7 @@ struct PlanEntry {
     // axis-0 split (plan_axis0_split): outputs [0, split_out) come from a sub-convolution whose tiles fit exactly, the rest
     // from a second one that the planner gives a shorter tile -- instead of a whole last tile that is mostly padding
     int64_t split_out = 0;
+    bool split_concurrent = false;   // run the tail on the second stream (only when it is a sizeable share of the work)
 };
 void PlanEntryDeleter::operator()(PlanEntry *e) const { if (e) { e->meta.release(); delete e; } }
 
@@ -460,6 +468,9 @@ static void plan_axis0_split(const ndconv_problem *pr, const Geom &g, const FftP
     for (int a = 0; a < g.ndim; a++) samples *= (double)g.P[a];
     if (samples < 4.0e6 || (full - split) * 64 < full) return;              // three more launches must buy at least 1.5 % of the rows
     e->split_out = o_split;
+    // measured: a tail of ~10 % of the rows (one rank of c5 on 8 GPUs) gains 7.5 % from running beside the main part, a tail
+    // of ~1 % (c5 on one GPU) loses 2 % (its CTAs delay a few CTAs of the main part's persistent grids)
+    e->split_concurrent = (int64_t)tb.ntiles * tb.F * 25 >= split;
 #else
     (void)pr; (void)g; (void)pl;
 #endif
@@ -1049,14 +1060,17 @@ static int conv_fft_fast(ndconv_processor *p, const ndconv_problem *pr, const Ge
         cp.tw = twc;
         return launch_raw(p->lc(), name, bytes, [&] { launch_col(pl.tl[axis].F, cp, p->num_sms, stm); });
     };
+    // launches of a tail part that runs beside the main part on the second stream are profiled under their own names: their
+    // event-to-event durations include the time they wait for SMs
+    const bool tail = p->on_aux;
     rp.nwork = pl.ntiles_total * rows_per_tile;
-    st = launch_raw(p->lc(), "row_fwd_pad_r2c", in_bytes + S * csz, [&] { row_launch(false); }); if (st) return st;
-    for (int a = al - 1; a >= 1; a--) { st = col_launch(a, 0, "col_fwd", 2 * S * csz); if (st) return st; }
-    st = col_launch(0, 2, "col_fwd_mul_inv", 2 * S * csz + (double)tile_elems * csz); if (st) return st;
-    for (int a = 1; a <= al - 1; a++) { st = col_launch(a, 1, "col_inv", 2 * S * csz); if (st) return st; }
+    st = launch_raw(p->lc(), tail ? "tail:row_fwd_pad_r2c" : "row_fwd_pad_r2c", in_bytes + S * csz, [&] { row_launch(false); }); if (st) return st;
+    for (int a = al - 1; a >= 1; a--) { st = col_launch(a, 0, tail ? "tail:col_fwd" : "col_fwd", 2 * S * csz); if (st) return st; }
+    st = col_launch(0, 2, tail ? "tail:col_fwd_mul_inv" : "col_fwd_mul_inv", 2 * S * csz + (double)tile_elems * csz); if (st) return st;
+    for (int a = 1; a <= al - 1; a++) { st = col_launch(a, 1, tail ? "tail:col_inv" : "col_inv", 2 * S * csz); if (st) return st; }
     rp.nwork = pl.tl[al].ntiles;
     for (int a = 0; a < al; a++) rp.nwork *= g.O[a];
-    st = launch_raw(p->lc(), "row_inv_c2r_crop", So * csz + out_bytes, [&] { row_launch(true); }); if (st) return st;
+    st = launch_raw(p->lc(), tail ? "tail:row_inv_c2r_crop" : "row_inv_c2r_crop", So * csz + out_bytes, [&] { row_launch(true); }); if (st) return st;
     return NDCONV_OK;
 }
 #endif
@@ -1085,13 +1099,43 @@ static int conv_fft_t(ndconv_processor *p, const ndconv_problem *pr, PlanEntry *
         ndconv_problem base = *pr;
         base.memory = NDCONV_MEM_DEVICE; base.data = dev_x;
         for (int a = 0; a < N; a++) base.data_strides[a] = gc.xstr[a];
-        ndconv_problem sub = base;
-        sub.data_shape[0] = rowsA; sub.pad[0][1] = 0; sub.border[0][1].type = NDCONV_BORDER_ZEROS;
-        st = conv_fft_impl(p, &sub, dev_out); if (st) return st;
-        sub = base;
-        sub.data = (const char *)dev_x + (pB - gc.pf[0]) * gc.xstr[0] * (int64_t)gc.es;
-        sub.data_shape[0] = gc.n[0] - (pB - gc.pf[0]); sub.pad[0][0] = 0; sub.border[0][0].type = NDCONV_BORDER_ZEROS;
-        st = conv_fft_impl(p, &sub, (char *)dev_out + (size_t)o_split * (size_t)out_row * gc.es); if (st) return st;
+        ndconv_problem subA = base, subB = base;
+        subA.data_shape[0] = rowsA; subA.pad[0][1] = 0; subA.border[0][1].type = NDCONV_BORDER_ZEROS;
+        subB.data = (const char *)dev_x + (pB - gc.pf[0]) * gc.xstr[0] * (int64_t)gc.es;
+        subB.data_shape[0] = gc.n[0] - (pB - gc.pf[0]); subB.pad[0][0] = 0; subB.border[0][0].type = NDCONV_BORDER_ZEROS;
+        void *outB = (char *)dev_out + (size_t)o_split * (size_t)out_row * gc.es;
+        bool concurrent = false;
+#ifdef NDCONV_CUDA
+        // The tail's launches are small (ramp and tail dominate them: measured ~65 % of the big launches' rate), so they run on
+        // a second stream with their own workspace and fill the idle SMs at the ends of the main part's kernels.  Every cache
+        // fill (plans, twiddles, kernel spectra) is synchronous on the host, so the two streams only share read-only state.
+        static const bool sequential = getenv("NDCONV_SPLIT_SEQUENTIAL") != nullptr;
+        concurrent = !sequential && !p->in_split && pe->split_concurrent;
+        if (concurrent) {
+            if (!p->aux_stream) {
+                CU_CHECK(cudaStreamCreateWithFlags(&p->aux_stream, cudaStreamNonBlocking));
+                CU_CHECK(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
+                CU_CHECK(cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming));
+            }
+            CU_CHECK(cudaEventRecord(p->ev_fork, p->stream));               // the input (and the staging copy above) is ready on the main stream
+            CU_CHECK(cudaStreamWaitEvent(p->aux_stream, p->ev_fork, 0));
+            p->in_split = true;
+            st = conv_fft_impl(p, &subA, dev_out);
+            if (!st) {
+                std::swap(p->stream, p->aux_stream); std::swap(p->ws, p->ws_aux); p->on_aux = true;
+                st = conv_fft_impl(p, &subB, outB);
+                std::swap(p->stream, p->aux_stream); std::swap(p->ws, p->ws_aux); p->on_aux = false;
+            }
+            p->in_split = false;
+            if (st) return st;
+            CU_CHECK(cudaEventRecord(p->ev_join, p->aux_stream));
+            CU_CHECK(cudaStreamWaitEvent(p->stream, p->ev_join, 0));
+        }
+#endif
+        if (!concurrent) {
+            st = conv_fft_impl(p, &subA, dev_out); if (st) return st;
+            st = conv_fft_impl(p, &subB, outB); if (st) return st;
+        }
         if (pr->memory == NDCONV_MEM_HOST) {
             st = be_d2h(out, dev_out, obytes, p->stream); if (st) return st;
             st = be_sync(p->stream); if (st) return st;
@@ -1507,8 +1551,11 @@ int ndconv_processor_destroy(ndconv_processor *p)
     be_sync(p->stream);
     p->ws.release(); p->in_stage.release(); p->out_stage.release(); p->meta.release(); p->kb_stage.release(); p->kmeta.release();
     for (int b = 0; b < 2; b++) { p->pipe_in[b].release(); p->pipe_out[b].release(); }
-    p->pipe_row.release(); p->zero_map.release();
+    p->pipe_row.release(); p->zero_map.release(); p->ws_aux.release();
 #ifdef NDCONV_CUDA
+    if (p->aux_stream) { cudaStreamSynchronize(p->aux_stream); cudaStreamDestroy(p->aux_stream); }
+    if (p->ev_fork) cudaEventDestroy(p->ev_fork);
+    if (p->ev_join) cudaEventDestroy(p->ev_join);
     if (p->h2d_stream) cudaStreamDestroy(p->h2d_stream);
     if (p->d2h_stream) cudaStreamDestroy(p->d2h_stream);
     for (int b = 0; b < 2; b++) { if (p->ev_h2d[b]) cudaEventDestroy(p->ev_h2d[b]); if (p->ev_comp[b]) cudaEventDestroy(p->ev_comp[b]); if (p->ev_d2h[b]) cudaEventDestroy(p->ev_d2h[b]); }
