@@ -173,7 +173,7 @@ struct ndconv_processor {
     // axis-0 split: the tail part runs on a second stream with a workspace of its own, beside the main part
     DevBuf ws_aux;
     stream_t aux_stream = nullptr;
-    bool in_split = false, on_aux = false;   // on_aux: the launches being issued belong to the tail part on the second stream
+    bool in_split = false, in_tail = false;  // in_tail: the launches being issued belong to the tail part (profiled under tail:* names)
 #ifdef NDCONV_CUDA
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 #endif
@@ -1060,9 +1060,9 @@ static int conv_fft_fast(ndconv_processor *p, const ndconv_problem *pr, const Ge
         cp.tw = twc;
         return launch_raw(p->lc(), name, bytes, [&] { launch_col(pl.tl[axis].F, cp, p->num_sms, stm); });
     };
-    // launches of a tail part that runs beside the main part on the second stream are profiled under their own names: their
-    // event-to-event durations include the time they wait for SMs
-    const bool tail = p->on_aux;
+    // launches of the tail part of an axis-0 split are profiled under their own names: per-launch figures of the main kernels stay
+    // comparable, and when the tail runs beside the main part its event-to-event durations include the time it waits for SMs
+    const bool tail = p->in_tail;
     rp.nwork = pl.ntiles_total * rows_per_tile;
     st = launch_raw(p->lc(), tail ? "tail:row_fwd_pad_r2c" : "row_fwd_pad_r2c", in_bytes + S * csz, [&] { row_launch(false); }); if (st) return st;
     for (int a = al - 1; a >= 1; a--) { st = col_launch(a, 0, tail ? "tail:col_fwd" : "col_fwd", 2 * S * csz); if (st) return st; }
@@ -1122,9 +1122,11 @@ static int conv_fft_t(ndconv_processor *p, const ndconv_problem *pr, PlanEntry *
             p->in_split = true;
             st = conv_fft_impl(p, &subA, dev_out);
             if (!st) {
-                std::swap(p->stream, p->aux_stream); std::swap(p->ws, p->ws_aux); p->on_aux = true;
+                std::swap(p->stream, p->aux_stream); std::swap(p->ws, p->ws_aux);
+                p->in_tail = true;
                 st = conv_fft_impl(p, &subB, outB);
-                std::swap(p->stream, p->aux_stream); std::swap(p->ws, p->ws_aux); p->on_aux = false;
+                p->in_tail = false;
+                std::swap(p->stream, p->aux_stream); std::swap(p->ws, p->ws_aux);
             }
             p->in_split = false;
             if (st) return st;
@@ -1134,7 +1136,10 @@ static int conv_fft_t(ndconv_processor *p, const ndconv_problem *pr, PlanEntry *
 #endif
         if (!concurrent) {
             st = conv_fft_impl(p, &subA, dev_out); if (st) return st;
-            st = conv_fft_impl(p, &subB, outB); if (st) return st;
+            p->in_tail = true;
+            st = conv_fft_impl(p, &subB, outB);
+            p->in_tail = false;
+            if (st) return st;
         }
         if (pr->memory == NDCONV_MEM_HOST) {
             st = be_d2h(out, dev_out, obytes, p->stream); if (st) return st;
