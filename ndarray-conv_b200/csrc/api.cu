@@ -1217,7 +1217,7 @@ static int conv_fft_impl(ndconv_processor *p, const ndconv_problem *pr, void *ou
 // filled), which is exactly "pad axis 0 first" of the reference's sequential definition (src/padding/mod.rs:119-153),
 // so the slab runs as a plain device problem with no axis-0 border.
 static const size_t kPipelineMinBytes = 96u << 20;
-static const size_t kPipelineSlabBytes = 160u << 20;
+static const size_t kPipelineSlabBytes = 64u << 20;      // measured on c5: 160 MB 102.0 ms, 64 MB 100.0 ms, 32 MB 102.4 ms per step (fill + drain vs per-slab overhead)
 
 static bool pipeline_eligible(const ndconv_problem *pr, const Geom &g)
 {
@@ -1245,9 +1245,14 @@ static int conv_fft_host_pipelined(ndconv_processor *p, const ndconv_problem *pr
     const size_t in_row_bytes = (size_t)in_row_elems * g.es, out_row_bytes = (size_t)out_row_elems * g.es;
     // slab height in output rows: a multiple of the axis-0 tile payload so no tile is cut
     FftPlan fullpl; st = make_plan(g, &fullpl); if (st) return st;
-    const int64_t V0 = std::max<int64_t>(1, fullpl.tl[0].V / g.s[0]);
+    int64_t V0 = std::max<int64_t>(1, fullpl.tl[0].V / g.s[0]);
     static const size_t slab_bytes = getenv("NDCONV_PIPE_SLAB_MB") ? (size_t)atoll(getenv("NDCONV_PIPE_SLAB_MB")) << 20 : kPipelineSlabBytes;   // experiments
     int64_t rows = (int64_t)(slab_bytes / std::max<size_t>(1, std::max(in_row_bytes * g.s[0], out_row_bytes)));
+    if (fullpl.fast && rows < V0) {
+        // a slab shorter than one tile row of the full plan: take the payload of the largest power-of-two tile that fits the budget
+        // (the slab's own plan picks that tile); shorter slabs shorten the fill and drain of the three-stage pipeline
+        for (int F = fullpl.tl[0].F / 2; F >= 64 && rows < V0; F /= 2) { const int64_t v = (F - g.Kd[0] + 1) / g.s[0]; if (v >= 1 && 2 * (F - g.Kd[0] + 1) >= F) V0 = v; else break; }
+    }
     rows = std::max<int64_t>(V0, rows / V0 * V0);
     if (rows >= g.O[0]) rows = std::max<int64_t>(1, (g.O[0] + 1) / 2);
     const int64_t nslab = (g.O[0] + rows - 1) / rows;
