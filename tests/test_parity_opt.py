@@ -137,3 +137,80 @@ def test_pipelined_host_path(pkg, cuda_lib, oracle, padding):
     assert got.shape == ref.shape
     assert np.max(np.abs(got - ref)) <= fft_tol(np.float32, 1024 * 2048, ref)
     proc.close()
+
+
+def _random_fast_case(rng):
+    """a random problem sized for the sm_100a fast path (rank 1-3, f32 or Complex<f32>), borders inside the reference's
+    non-panicking domain"""
+    nd = int(rng.integers(1, 4))
+    if nd == 1:
+        shape = [int(rng.integers(600, 200000))]
+    elif nd == 2:
+        n1 = int(rng.integers(130, 3000))
+        shape = [int(rng.integers(20, max(21, min(1500, 2_000_000 // n1)))), n1]
+    else:
+        n2 = int(rng.integers(130, 600)); n1 = int(rng.integers(16, 200))
+        shape = [int(rng.integers(4, max(5, min(60, 2_000_000 // (n1 * n2))))), n1, n2]
+    ks = [int(rng.integers(1, 8)) for _ in range(nd)]
+    ks[-1] = int(rng.integers(1, 40))
+    dil = [int(rng.integers(1, 4)) for _ in range(nd)]
+    kd = [(k - 1) * d + 1 for k, d in zip(ks, dil)]
+    kind = int(rng.integers(0, 5))
+    if kind < 3:
+        mode = ["full", "same", "valid"][kind]
+        pads = {"full": [[v - 1, v - 1] for v in kd], "same": [[v // 2, (v - 1) // 2] for v in kd], "valid": [[0, 0]] * nd}[mode]
+    elif kind == 3:
+        pp = [int(rng.integers(0, 12)) for _ in range(nd)]
+        mode = ("custom", pp, [int(rng.integers(1, 4)) for _ in range(nd)])
+        pads = [[q, q] for q in pp]
+    else:
+        pads = [[int(rng.integers(0, 12)), int(rng.integers(0, 12))] for _ in range(nd)]
+        mode = ("explicit", pads, [int(rng.integers(1, 4)) for _ in range(nd)])
+    if any(shape[i] + pads[i][0] + pads[i][1] < kd[i] for i in range(nd)):
+        return None
+    names = ["zeros", ("const", 1.25), "reflect", "replicate", "circular"]
+    sides = []
+    for i in range(nd):
+        row = []
+        for sd in range(2):
+            b = names[int(rng.integers(0, 5))]
+            if pads[i][sd] > shape[i] - 1 and b in ("reflect", "circular"):
+                b = "replicate"
+            row.append(b)
+        sides.append(row)
+    pk = int(rng.integers(0, 3))
+    padding = ("explicit", sides) if pk == 0 else (("custom", [r[0] if max(pads[i]) <= shape[i] - 1 or r[0] not in ("reflect", "circular") else "replicate" for i, r in enumerate(sides)]) if pk == 1 else
+                                                 (sides[0][0] if all(max(pads[i]) <= shape[i] - 1 for i in range(nd)) or sides[0][0] not in ("reflect", "circular") else "zeros"))
+    cx = nd >= 2 and bool(rng.integers(0, 3) == 0)
+    return shape, ks, dil, mode, padding, bool(rng.integers(0, 2)), cx
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_fast_path_random(pkg, cuda_lib, oracle, seed):
+    rng = np.random.default_rng(900 + seed)
+    proc = pkg.get_fft_processor(0, cuda_lib)
+    done = 0
+    while done < 16:
+        case = _random_fast_case(rng)
+        if case is None:
+            continue
+        shape, ks, dil, mode, padding, rev, cx = case
+        if cx:
+            x = ((rng.random(shape) - 0.5) + 1j * (rng.random(shape) - 0.5)).astype(np.complex64)
+            k = ((rng.random(ks) - 0.5) + 1j * (rng.random(ks) - 0.5)).astype(np.complex64)
+        else:
+            x = (rng.random(shape, dtype=np.float32) - 0.5)
+            k = (rng.random(ks, dtype=np.float32) - 0.5)
+        try:
+            ref = oracle.conv_f64_truth(x, k, mode, padding, dil, rev)
+        except oracle.OracleError:
+            continue
+        kw = pkg.with_dilation(k, dil)
+        if not rev:
+            kw = kw.no_reverse()
+        got = pkg.conv_fft_with_processor(x, kw, mode_from_spec(pkg, mode), padding_from_spec(pkg, padding), proc)
+        assert got.shape == ref.shape, case
+        tol = fft_tol(x.dtype, 1024 * 2048, ref, float(np.max(np.abs(x)) * np.sum(np.abs(k))))
+        assert np.max(np.abs(got - ref)) <= tol, (case, float(np.max(np.abs(got - ref))), tol)
+        done += 1
+    proc.close()
