@@ -432,7 +432,7 @@ struct PlanEntry {
     FftPlan pl;
     // axis-0 split (plan_axis0_split): outputs [0, split_out) come from a sub-convolution whose tiles fit exactly, the rest
     // from a second one that the planner gives a shorter tile -- instead of a whole last tile that is mostly padding
-    int64_t split_out = 0;
+    int64_t split_out = 0, split_rows_a = 0;   // outputs / input rows of part A
     bool split_concurrent = false;   // run the tail on the second stream (only when it is a sizeable share of the work)
 };
 void PlanEntryDeleter::operator()(PlanEntry *e) const { if (e) { e->meta.release(); delete e; } }
@@ -451,7 +451,19 @@ static void plan_axis0_split(const ndconv_problem *pr, const Geom &g, const FftP
     const AxisTiling &t = pl.tl[0];
     if (t.ntiles < 2) return;
     if ((g.bf[0] == NDCONV_BORDER_CIRCULAR && g.pf[0] > 0) || (g.bb[0] == NDCONV_BORDER_CIRCULAR && g.pb[0] > 0)) return;
-    const int64_t covered = (int64_t)(t.ntiles - 1) * t.V;                  // padded positions whose outputs the full tiles produce
+    // part A = the first m tile rows.  Two reasons to cut:
+    //  (1) workspace budget: one tile row of workspace per tile row of the problem adds up (c5: 5 GB; a 131072^2 array: 80 GB on
+    //      top of 64 GB in and 64 GB out -- more than the 180 GB of a B200), so a plan whose workspace exceeds the budget is
+    //      processed in stripes of as many tile rows as fit, one after the other through the same workspace;
+    //  (2) the tail: the last tile row is mostly padding, part B gets a shorter tile.
+    static const double budget = getenv("NDCONV_WS_BUDGET_MB") ? atof(getenv("NDCONV_WS_BUDGET_MB")) * 1048576.0 : 24.0 * 1073741824.0;
+    const int al = g.ndim - 1;
+    double ws_tile_row = 8.0 * (pl.is_cx ? (double)pl.tl[al].F : (double)(pl.tl[al].F / 2 + 8)) * (double)pl.tl[al].ntiles;
+    for (int a = 0; a < al; a++) ws_tile_row *= (double)pl.tl[a].F * (a > 0 ? (double)pl.tl[a].ntiles : 1.0);
+    int64_t m = t.ntiles - 1;
+    const bool over_budget = ws_tile_row * (double)t.ntiles > budget;
+    if (over_budget) m = std::max<int64_t>(1, std::min<int64_t>(t.ntiles - 1, (int64_t)(budget / ws_tile_row)));
+    const int64_t covered = m * t.V;                                        // padded positions whose outputs part A produces
     const int64_t o_split = (covered + g.s[0] - 1) / g.s[0];
     if (o_split <= 0 || o_split >= g.O[0]) return;
     const int64_t pB = o_split * g.s[0];                                    // first padded row part B reads
@@ -459,18 +471,21 @@ static void plan_axis0_split(const ndconv_problem *pr, const Geom &g, const FftP
     if (pB < g.pf[0] || rowsA < 1 || rowsA > g.n[0]) return;                // the cut must fall inside the array on both sides
     const int64_t rowsB = g.n[0] - (pB - g.pf[0]);
     if (rowsB < 1 || g.pb[0] >= rowsB || g.pf[0] >= rowsA) return;          // a border may not reach past the part that carries it
-    static const int menu_col[7] = {16, 32, 64, 128, 256, 512, 1024};
-    AxisTiling tb; tb.F = 0;
-    fast_pick_tile(g.P[0] - pB, g.Kd[0], menu_col, 7, &tb);
-    if (tb.F == 0) return;
-    const int64_t full = (int64_t)t.ntiles * t.F, split = (int64_t)(t.ntiles - 1) * t.F + (int64_t)tb.ntiles * tb.F;
-    double samples = 1.0;
-    for (int a = 0; a < g.ndim; a++) samples *= (double)g.P[a];
-    if (samples < 4.0e6 || (full - split) * 64 < full) return;              // three more launches must buy at least 1.5 % of the rows
+    if (!over_budget) {
+        static const int menu_col[7] = {16, 32, 64, 128, 256, 512, 1024};
+        AxisTiling tb; tb.F = 0;
+        fast_pick_tile(g.P[0] - pB, g.Kd[0], menu_col, 7, &tb);
+        if (tb.F == 0) return;
+        const int64_t full = (int64_t)t.ntiles * t.F, split = (int64_t)(t.ntiles - 1) * t.F + (int64_t)tb.ntiles * tb.F;
+        double samples = 1.0;
+        for (int a = 0; a < g.ndim; a++) samples *= (double)g.P[a];
+        if (samples < 4.0e6 || (full - split) * 64 < full) return;          // three more launches must buy at least 1.5 % of the rows
+        // measured: a tail of ~10 % of the rows (one rank of c5 on 8 GPUs) gains 7.5 % from running beside the main part, a tail
+        // of ~1 % (c5 on one GPU) loses 2 % (its CTAs delay a few CTAs of the main part's persistent grids)
+        e->split_concurrent = (int64_t)tb.ntiles * tb.F * 25 >= split;
+    } else e->split_concurrent = false;                                     // stripes share one workspace: one after the other
     e->split_out = o_split;
-    // measured: a tail of ~10 % of the rows (one rank of c5 on 8 GPUs) gains 7.5 % from running beside the main part, a tail
-    // of ~1 % (c5 on one GPU) loses 2 % (its CTAs delay a few CTAs of the main part's persistent grids)
-    e->split_concurrent = (int64_t)tb.ntiles * tb.F * 25 >= split;
+    e->split_rows_a = rowsA;
 #else
     (void)pr; (void)g; (void)pl;
 #endif
@@ -1090,7 +1105,7 @@ static int conv_fft_t(ndconv_processor *p, const ndconv_problem *pr, PlanEntry *
         // two device-resident sub-convolutions along axis 0 (plan_axis0_split); each has its own cached plan
         const Geom gc = pe->g;                      // copies: the nested calls may evict this entry
         const int64_t o_split = pe->split_out, pB = o_split * gc.s[0];
-        const int64_t rowsA = (int64_t)(pe->pl.tl[0].ntiles - 1) * pe->pl.tl[0].V + gc.Kd[0] - 1 - gc.pf[0];
+        const int64_t rowsA = pe->split_rows_a;
         const size_t obytes = (size_t)gc.out_total * gc.es;
         void *dev_out = out;
         if (pr->memory == NDCONV_MEM_HOST) { st = p->out_stage.reserve(obytes); if (st) return st; dev_out = p->out_stage.p; }

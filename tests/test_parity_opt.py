@@ -119,6 +119,31 @@ def test_opt2d_matches_generic_path(pkg, cuda_lib):
     assert np.max(np.abs(outs[0] - outs[1])) <= 8 * np.finfo(np.float32).eps * np.log2(1024 * 2048) * scale
 
 
+def test_workspace_budget_stripes(pkg, cuda_lib):
+    """a plan whose workspace exceeds the budget (NDCONV_WS_BUDGET_MB, default 24 GB) is processed in stripes of tile rows through
+    one workspace: the striped result must equal the unstriped one bit for bit (same tiles, same kernels)"""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import importlib,numpy as np,sys; sys.path.insert(0,'.');"
+        "pkg=importlib.import_module('ndarray-conv_b200');"
+        "rng=np.random.default_rng(5); x=rng.random((3000,2600),dtype=np.float32)-0.5; k=rng.random((7,9),dtype=np.float32);"
+        "p=pkg.get_fft_processor(0);"
+        "y=pkg.conv_fft_with_processor(x,k,pkg.ConvMode.Custom([5,3],[2,1]),pkg.PaddingMode.Custom([pkg.BorderType.Replicate,pkg.BorderType.Reflect]),p);"
+        "np.save(sys.argv[1],y); print('WS', p.workspace_bytes)"
+    )
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs, ws = [], []
+    for tag, env in (("full", {"NDCONV_DISABLE_SPLIT": "1"}), ("striped", {"NDCONV_WS_BUDGET_MB": "20"})):
+        path = f"/tmp/ndconv_ws_{tag}.npy"
+        r = subprocess.run([sys.executable, "-c", code, path], check=True, cwd=root, env={**os.environ, **env}, capture_output=True, text=True)
+        outs.append(np.load(path))
+        ws.append(int(r.stdout.split("WS")[1].split()[0]))
+    assert np.array_equal(outs[0], outs[1])
+    assert ws[0] - ws[1] >= 20 << 20, ws   # all device buffers of the processor: three tile rows of workspace (3 x 16.9 MB) against one (measured 96.6 vs 69.0 MB)
+
+
 @pytest.mark.parametrize("padding", ["reflect", ("custom", ["circular", "replicate"]), ("explicit", [[("const", 2.0), "replicate"], ["zeros", "reflect"]])],
                          ids=["reflect", "circular-replicate", "const-mixed"])
 def test_pipelined_host_path(pkg, cuda_lib, oracle, padding):
