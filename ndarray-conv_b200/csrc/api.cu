@@ -348,7 +348,7 @@ static bool fast_eligible(const Geom &g)
 #ifdef NDCONV_CUDA
     static const bool disabled = getenv("NDCONV_DISABLE_OPT") != nullptr;
     const bool cx32 = g.dtype == NDCONV_C32;
-    if (disabled || (g.dtype != NDCONV_F32 && !cx32) || g.ndim < (cx32 ? 2 : 1) || g.ndim > 3) return false;
+    if (disabled || (g.dtype != NDCONV_F32 && !cx32) || g.ndim < 1 || g.ndim > 3) return false;
     const int al = g.ndim - 1;
     if (g.P[al] < (cx32 ? 64 : 128) || g.Kd[al] > (cx32 ? 512 : 1024)) return false;
     int64_t tot = 1;
@@ -953,6 +953,12 @@ template <int T> static void launch_row_cx(bool inverse, const fast::RowParams &
     if (rp.ndim == 2) launch_row_cx_n<T, 2>(inverse, rp, grid, stm);
     else launch_row_cx_n<T, 3>(inverse, rp, grid, stm);
 }
+template <int T> static void launch_row1d_cx(const fast::RowParams &rp, int grid, stream_t stm)
+{
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(fast::row1d_c<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, fast::Row1dCxCfg<T>::smem); attr = true; }
+    fast::row1d_c<T><<<grid, 128, fast::Row1dCxCfg<T>::smem, stm>>>(rp);
+}
 template <int T> static void launch_row1d(const fast::RowParams &rp, int grid, stream_t stm)
 {
     static bool attr = false;
@@ -1028,7 +1034,16 @@ static int conv_fft_fast(ndconv_processor *p, const ndconv_problem *pr, const Ge
         const int64_t items = (rp.nwork + (32 / T) - 1) / (32 / T);
         const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((items + 3) / 4, (int64_t)p->num_sms * 3 * 8));
         const stream_t stm1 = p->stream;
-        return launch_raw(p->lc(), "row1d_fwd_mul_inv", 4.0 * (double)g.data_total + 4.0 * (double)g.out_total, [&] {
+        return launch_raw(p->lc(), "row1d_fwd_mul_inv", (double)g.es * ((double)g.data_total + (double)g.out_total), [&] {
+            if (is_cx) {
+                switch (T) {
+                case 32: launch_row1d_cx<32>(rp, grid, stm1); break;
+                case 16: launch_row1d_cx<16>(rp, grid, stm1); break;
+                case 8: launch_row1d_cx<8>(rp, grid, stm1); break;
+                default: launch_row1d_cx<4>(rp, grid, stm1); break;
+                }
+                return;
+            }
             switch (T) {
             case 32: launch_row1d<32>(rp, grid, stm1); break;
             case 16: launch_row1d<16>(rp, grid, stm1); break;

@@ -697,6 +697,98 @@ __global__ void __launch_bounds__(128, 3) row1d(const __grid_constant__ RowParam
     }
 }
 
+// ---- rank 1, Complex<f32>: forward C2C, multiply by the kernel spectrum, inverse C2C, crop -- one pass, no workspace ----------------
+template <int T> struct Row1dCxCfg { static constexpr int L = 32 * T, smem = (L + L + 4 * RowCfg<T>::wstride) * 8; };
+
+template <int T>
+__global__ void __launch_bounds__(128, 4) row1d_c(const __grid_constant__ RowParams p)
+{
+    constexpr int L = RowCfg<T>::L, M = RowCfg<T>::M, G = RowCfg<T>::G;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    pc *s_twF = reinterpret_cast<pc *>(smem_raw);         // s_twF[k1 * T + t] = W_L^{t k1}
+    pc *s_twI = s_twF + L;                                // s_twI[i * 32 + k1] = W_L^{i k1}
+    pc *s_ex = s_twI + L;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane / T, t = lane % T;
+    for (int idx = threadIdx.x; idx < L; idx += blockDim.x) {
+        s_twF[idx] = ld_pc(p.tw + (idx / T) * (idx % T));
+        s_twI[idx] = ld_pc(p.tw + (idx >> 5) * (idx & 31));
+    }
+    __syncthreads();
+    pc *sb = s_ex + warp * RowCfg<T>::wstride + g * RowCfg<T>::gstride;
+    const cf *xc = reinterpret_cast<const cf *>(p.x);
+    cf *outc = reinterpret_cast<cf *>(p.out);
+    const int64_t nwarp_items = (p.nwork + G - 1) / G;
+    for (int64_t wi = (int64_t)blockIdx.x * 4 + warp; wi < nwarp_items; wi += (int64_t)gridDim.x * 4) {
+        const int64_t tl = wi * G + g;
+        const bool active = tl < p.nwork;
+        const int64_t cl0 = tl * p.V[0];
+        pc v[32];
+        const bool interior = active && p.xstr[0] == 1 && cl0 >= p.pf[0] && cl0 + L <= p.pf[0] + p.n[0];
+        if (interior) {
+            const cf *src = xc + (cl0 - p.pf[0]);
+#pragma unroll
+            for (int j = 0; j < 32; j++) v[j].v = __ldg(reinterpret_cast<const unsigned long long *>(src + t + T * j));
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; j++) {
+                const int64_t cl = cl0 + t + T * j;
+                pc val = pk::mk(0.f, 0.f);
+                if (active && cl < p.P[0]) {
+                    const int64_t cc = cl - p.pf[0];
+                    if (cc >= 0 && cc < p.n[0]) val.v = __ldg(reinterpret_cast<const unsigned long long *>(xc + cc * p.xstr[0]));
+                    else {
+                        const int32_t m = p.map[0][cl];
+                        if (m == NDC_MAP_CONST_FRONT) val = pk::mk(p.cfront[0], p.cfront_im[0]);
+                        else if (m == NDC_MAP_CONST_BACK) val = pk::mk(p.cback[0], p.cback_im[0]);
+                        else if (m != NDC_MAP_INIT) val.v = __ldg(reinterpret_cast<const unsigned long long *>(xc + (int64_t)m * p.xstr[0]));
+                    }
+                }
+                v[j] = val;
+            }
+        }
+        pk::dft<false, 32>(v);
+#pragma unroll
+        for (int k1 = 0; k1 < 32; k1++) sb[k1 * (T + 1) + t] = pk::cmul(v[k1], s_twF[k1 * T + t]);
+        __syncwarp();
+#pragma unroll
+        for (int m = 0; m < M; m++)
+#pragma unroll
+            for (int i = 0; i < T; i++) v[m * T + i] = sb[(t + T * m) * (T + 1) + i];
+        __syncwarp();
+#pragma unroll
+        for (int m = 0; m < M; m++) pk::dft<false, T>(v + m * T);         // v[m*T + k2] = X[k], k = t + T m + 32 k2
+#pragma unroll
+        for (int m = 0; m < M; m++)
+#pragma unroll
+            for (int k2 = 0; k2 < T; k2++) v[m * T + k2] = pk::cmul(v[m * T + k2], ld_pc(p.kfast + t + T * m + 32 * k2));
+#pragma unroll
+        for (int m = 0; m < M; m++) pk::dft<true, T>(v + m * T);
+#pragma unroll
+        for (int m = 0; m < M; m++)
+#pragma unroll
+            for (int i = 0; i < T; i++) sb[(t + T * m) * (T + 1) + i] = pk::cmulc(v[m * T + i], s_twI[i * 32 + (t + T * m)]);
+        __syncwarp();
+#pragma unroll
+        for (int k1 = 0; k1 < 32; k1++) v[k1] = sb[k1 * (T + 1) + t];
+        __syncwarp();
+        pk::dft<true, 32>(v);                                            // v[j] = y[t + T j]
+        if (!active) continue;
+        const int Kd1 = p.Kd[0];
+        const int64_t mbase = tl * p.V[0];
+        const int64_t s1 = p.s[0];
+#pragma unroll
+        for (int j = 0; j < 32; j++) {
+            const int i = t + T * j;
+            if (i < Kd1 - 1) continue;
+            const int64_t q = mbase + i - (Kd1 - 1);
+            const int64_t o = s1 == 1 ? q : q / s1;
+            if (s1 != 1 && o * s1 != q) continue;
+            if (o < p.O[0]) st_pc(outc + o, v[j]);
+        }
+    }
+}
+
 // ---- column pass: FWD / INV / FMI ---------------------------------------------------------------------------------------------
 struct ColParams {
     cf *ws;

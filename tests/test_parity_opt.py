@@ -75,6 +75,11 @@ CX_CASES = [
     ((1025, 1030), (63, 63), 1, "valid", ("const", 0.25 + 2j), True),
     ((40, 90, 130), (3, 4, 5), 1, "full", ("custom", ["reflect", ("const", -1j), "circular"]), False),
     ((64, 64), (3, 3), 1, "same", "zeros", True),                                             # below the fast path's size threshold: generic kernels
+    # rank 1: fast::row1d_c
+    ((5000,), (31,), 1, "same", "zeros", True),
+    ((700,), (5,), 2, "full", ("const", 0.5 - 1j), False),
+    ((90000,), (400,), 1, ("custom", [7], [3]), "reflect", True),
+    ((3000,), (9,), 1, "valid", "circular", True),
 ]
 
 
@@ -206,7 +211,7 @@ def _random_fast_case(rng):
     pk = int(rng.integers(0, 3))
     padding = ("explicit", sides) if pk == 0 else (("custom", [r[0] if max(pads[i]) <= shape[i] - 1 or r[0] not in ("reflect", "circular") else "replicate" for i, r in enumerate(sides)]) if pk == 1 else
                                                  (sides[0][0] if all(max(pads[i]) <= shape[i] - 1 for i in range(nd)) or sides[0][0] not in ("reflect", "circular") else "zeros"))
-    cx = nd >= 2 and bool(rng.integers(0, 3) == 0)
+    cx = bool(rng.integers(0, 3) == 0)
     return shape, ks, dil, mode, padding, bool(rng.integers(0, 2)), cx
 
 
