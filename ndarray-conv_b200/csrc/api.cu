@@ -294,26 +294,6 @@ static void fill_consts(const ndconv_problem *pr, int ndim, unsigned char cf[][1
     }
 }
 
-// stage the data array on the device (host problems) or use it in place (device problems)
-static int stage_input(ndconv_processor *p, const ndconv_problem *pr, Geom &g, const void **dev_x)
-{
-    if (pr->memory == NDCONV_MEM_DEVICE) { *dev_x = pr->data; return NDCONV_OK; }
-    size_t bytes = (size_t)g.data_total * g.es;
-    int st = p->in_stage.reserve(bytes); if (st) return st;
-    if (g.data_contiguous) {
-        st = be_h2d(p->in_stage.p, pr->data, bytes, p->stream); if (st) return st;
-    } else {
-        std::vector<unsigned char> tmp(bytes);
-        pack_strided(pr->data, g.ndim, g.n, g.xstr, g.es, tmp.data());
-        st = be_h2d(p->in_stage.p, tmp.data(), bytes, p->stream); if (st) return st;
-        st = be_sync(p->stream); if (st) return st;
-    }
-    int64_t s = 1;
-    for (int i = g.ndim - 1; i >= 0; i--) { g.xstr[i] = s; s *= g.n[i]; }
-    *dev_x = p->in_stage.p;
-    return NDCONV_OK;
-}
-
 // ======================================================================================================
 // direct convolution
 // ======================================================================================================

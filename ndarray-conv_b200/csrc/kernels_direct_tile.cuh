@@ -110,8 +110,6 @@ __global__ void __launch_bounds__(kThreads) direct_tile_kernel(const __grid_cons
     const int64_t cx2_raw = c_lo[2] - p.pf[2];
     const int shift2 = (int)(((cx2_raw % kAlign) + kAlign) % kAlign);
     const int row_elems = p.IT2p, plane_elems = p.IT[1] * p.IT2p;
-    const int lane = tid & 31, warp = tid >> 5;
-    const int nrows = p.IT[0] * p.IT[1];
     const int64_t c2_lo = c_lo[2] - shift2;
 
     // window maps in shared memory: s_map[a][i] = border map of padded coordinate c_lo[a] + i (kBeyond outside [0, P[a]))
