@@ -164,9 +164,10 @@ int ndconv_conv_fft_par(ndconv_processor *p, const ndconv_problem *problem, void
  * [n0..n_{N-1}]; the spectrum has axis 0 moved to the end -- real input: [n1, .., n_{N-2}, n_{N-1}/2+1, n0], complex input:
  * [n1, .., n_{N-1}, n0] (N = 1: [n/2+1] / [n]).  forward is unnormalised (e^{-2 pi i ..}); backward divides by prod(shape)
  * (real.rs:278-279, complex.rs:141-142) and takes the original last-axis length from `shape` (the reference remembers it in
- * `rp_origin_len`, real.rs:41,108).  dtype F32/F64: real input, C32/C64: complex input.  This build takes {2,3,5,7}-smooth
- * lengths that fit one shared-memory transform per axis (last axis <= 8192 real / 4096 complex, even when real; other axes
- * <= 1024, f64: 512) and answers NDCONV_ERR_UNSUPPORTED otherwise (rustfft takes any length). */
+ * `rp_origin_len`, real.rs:41,108).  dtype F32/F64: real input, C32/C64: complex input.  Any length is taken, as rustfft
+ * does: an axis that is {2,3,5,7}-smooth and fits one shared-memory transform (last axis <= 8192 real / 4096 complex, even
+ * when real; other axes <= 1024, f64: 512) runs in the convolution pipeline's row / column kernels, every other axis (longer,
+ * odd real, prime factors above 7) as global-memory Stockham passes -- a prime factor r costs O(n r) there. */
 int ndconv_fft_forward(ndconv_processor *p, int dtype, int ndim, const int64_t *shape, const void *in, void *out, int memory);
 int ndconv_fft_backward(ndconv_processor *p, int dtype, int ndim, const int64_t *shape, const void *spectrum, void *out, int memory);
 

@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <limits>
 #include <map>
 #include <memory>
 #include <string>
@@ -1385,36 +1386,98 @@ static int conv_fft_impl(ndconv_processor *p, const ndconv_problem *pr, void *ou
 // ======================================================================================================
 // public N-d FFT of the processors: Processor::{forward, backward} (src/conv_fft/processor/mod.rs:91-118), with the
 // reference's rotated spectrum layout (real.rs:126-154, complex.rs:48-53): axis 0 ends up last.
-// Envelope of this build: {2,3,5,7}-smooth lengths that fit one shared-memory transform per axis.
+// Any length (rustfft / realfft take any, real.rs:40,62, complex.rs:56): an axis that is {2,3,5,7}-smooth and fits one
+// shared-memory transform (even, when it is the real axis) runs in the row / column kernels of the convolution pipeline;
+// every other axis -- longer, odd real, prime factors above 7 -- runs as global-memory Stockham passes (GPassBody).
 // ======================================================================================================
+// radices of the global passes: register butterflies first, every remaining prime factor as a generic pass
+static std::vector<int> global_radices(int64_t n, bool is_dbl)
+{
+    std::vector<int> r;
+    if (!is_dbl) while (n % 16 == 0 && n != 32) { r.push_back(16); n /= 16; }
+    while (n % 8 == 0) { r.push_back(8); n /= 8; }
+    while (n % 4 == 0) { r.push_back(4); n /= 4; }
+    while (n % 2 == 0) { r.push_back(2); n /= 2; }
+    for (int64_t f = 3; f * f <= n; f += 2) while (n % f == 0) { r.push_back((int)f); n /= f; }
+    if (n > 1) r.push_back((int)n);
+    return r;
+}
+
+// transform axis (outer, n, inner) of `*cur` into `*alt` pass by pass; on return *cur holds the result
+template <class R>
+static int run_global_axis(ndconv_processor *p, int64_t n, int64_t inner, int64_t outer, bool inverse, cx<R> **cur, cx<R> **alt, const char *name)
+{
+    if (n <= 1) return NDCONV_OK;
+    const cx<R> *tw = nullptr;
+    int st = get_tw_c<R>(p, (int)n, &tw); if (st) return st;
+    int64_t Ns = 1;
+    for (int r : global_radices(n, sizeof(R) == 8)) {
+        GPassParams<R> gp; memset(&gp, 0, sizeof(gp));
+        gp.in = *cur; gp.out = *alt; gp.n = n; gp.m = n / r; gp.Ns = Ns; gp.radix = r; gp.inner = inner; gp.outer = outer; gp.tw = tw; gp.inv = inverse ? 1 : 0;
+        const bool reg = r == 2 || r == 3 || r == 4 || r == 5 || r == 7 || r == 8 || r == 16;
+        gp.nwork = outer * inner * (reg ? gp.m : n);
+        const int64_t grid = std::min<int64_t>((gp.nwork + 255) / 256, (int64_t)p->num_sms * 16 * kMaxGridMult);
+        st = launch<GPassBody<R>, GPassParams<R>>(p->lc(), name, 2.0 * (double)(outer * n * inner) * sizeof(cx<R>), grid, 256, 0, gp); if (st) return st;
+        std::swap(*cur, *alt);
+        Ns *= r;
+    }
+    return NDCONV_OK;
+}
+
+template <class R>
+static int run_gmove(ndconv_processor *p, int mode, const void *src, void *dst, int64_t rows, int64_t n, int64_t spitch, int64_t dpitch, int64_t H, R scale, const char *name)
+{
+    GMoveParams<R> mp; memset(&mp, 0, sizeof(mp));
+    mp.src = src; mp.dst = dst; mp.rows = rows; mp.n = n; mp.spitch = spitch; mp.dpitch = dpitch; mp.H = H; mp.mode = mode; mp.scale = scale;
+    const int64_t total = rows * dpitch;
+    const int64_t grid = std::min<int64_t>((total + 255) / 256, (int64_t)p->num_sms * 16 * kMaxGridMult);
+    return launch<GMoveBody<R>, GMoveParams<R>>(p->lc(), name, (double)(rows * (spitch + dpitch)) * sizeof(cx<R>), grid, 256, 0, mp);
+}
+
 template <class R>
 static int fft_nd_t(ndconv_processor *p, bool is_cx, int N, const int64_t *shape, const void *in, void *out, int memory, bool inverse)
 {
     const bool is_dbl = sizeof(R) == 8;
     int64_t total = 1;
-    for (int a = 0; a < N; a++) { if (shape[a] < 1) { set_error("fft: empty axis"); return NDCONV_ERR_DATA_SHAPE; } total *= shape[a]; }
+    for (int a = 0; a < N; a++) {
+        if (shape[a] < 1) { set_error("fft: empty axis"); return NDCONV_ERR_DATA_SHAPE; }
+        if (shape[a] > std::numeric_limits<int32_t>::max()) { set_error("fft: axis longer than 2^31-1"); return NDCONV_ERR_UNSUPPORTED; }
+        total *= shape[a];
+    }
     FftPlan pl; pl.N = N; pl.is_cx = is_cx;
+    bool in_smem[NDC_MAX_DIM], any_col_global = false;
     for (int a = 0; a < N; a++) {
         const bool last = a == N - 1, real_axis = last && !is_cx;
         const int cap = last ? cap_last_axis(is_cx, is_dbl) : cap_col_axis(is_dbl);
-        if (shape[a] > cap || (real_axis && (shape[a] & 1))) { set_error("fft: axis length outside this build's envelope (<= one shared-memory transform, even real axis)"); return NDCONV_ERR_UNSUPPORTED; }
         pl.tl[a].F = (int)shape[a]; pl.tl[a].V = (int)shape[a]; pl.tl[a].ntiles = 1;
-        if (!factor_radices(real_axis ? (int)shape[a] / 2 : (int)shape[a], &pl.fl[a], is_dbl ? 16 : 32)) { set_error("fft: length is not {2,3,5,7}-smooth (Bluestein not implemented)"); return NDCONV_ERR_UNSUPPORTED; }
+        in_smem[a] = shape[a] <= cap && !(real_axis && (shape[a] & 1)) &&
+                     factor_radices(real_axis ? (int)shape[a] / 2 : (int)shape[a], &pl.fl[a], is_dbl ? 16 : 32);
+        if (!last && !in_smem[a]) any_col_global = true;
     }
-    const int Fl = pl.tl[N - 1].F;
-    pl.H = is_cx ? Fl : Fl / 2 + 1;
+    const int64_t Fl = shape[N - 1];
+    const bool last_global = !in_smem[N - 1];
+    pl.H = (int)(is_cx ? Fl : Fl / 2 + 1);
     pl.Hp = (int)align_up((size_t)pl.H, 16);
     pl.rows_per_tile = 1;
     for (int a = 0; a < N - 1; a++) pl.rows_per_tile *= pl.tl[a].F;
     pl.tile_elems = pl.rows_per_tile * pl.Hp; pl.ntiles_total = 1;
+    const int64_t rows = pl.rows_per_tile;
     const int es = (int)sizeof(R) * (is_cx ? 2 : 1);
-    const size_t real_bytes = (size_t)total * es, spec_elems = (size_t)(total / Fl) * pl.H, spec_bytes = spec_elems * sizeof(cx<R>);
+    const size_t real_bytes = (size_t)total * es, spec_elems = (size_t)rows * pl.H, spec_bytes = spec_elems * sizeof(cx<R>);
     int st = set_device(p); if (st) return st;
-    st = p->ws.reserve((size_t)pl.tile_elems * sizeof(cx<R>)); if (st) return st;
+    // one reservation: spectra workspace [rows][Hp], its ping-pong twin when a strided axis takes the global passes, and two
+    // dense [rows][Fl] complex buffers when the last axis does
+    const size_t ws_elems = (size_t)pl.tile_elems, row_elems = last_global ? (size_t)rows * (size_t)Fl : 0;
+    st = p->ws.reserve((ws_elems * (any_col_global ? 2 : 1) + 2 * row_elems) * sizeof(cx<R>)); if (st) return st;
+    cx<R> *ws_a = (cx<R> *)p->ws.p, *ws_b = any_col_global ? ws_a + ws_elems : nullptr;
+    cx<R> *row_a = ws_a + ws_elems * (any_col_global ? 2 : 1), *row_b = row_a + row_elems;
     // identity border maps (no padding)
     Geom g; g.ndim = N; g.es = es;
     std::vector<int32_t> maps[NDC_MAX_DIM];
-    for (int a = 0; a < N; a++) { maps[a].resize((size_t)shape[a]); for (int64_t i = 0; i < shape[a]; i++) maps[a][(size_t)i] = (int32_t)i; }
+    for (int a = 0; a < N; a++) {
+        maps[a].resize(last_global ? 1 : (size_t)shape[a]);       // the row kernels are the only readers of the maps
+        for (size_t i = 0; i < maps[a].size(); i++) maps[a][i] = (int32_t)i;
+    }
     MetaLayout ml;
     st = upload_meta(p, p->kmeta, g, maps, nullptr, &ml); if (st) return st;
     st = be_sync(p->stream); if (st) return st;
@@ -1435,24 +1498,50 @@ static int fft_nd_t(ndconv_processor *p, bool is_cx, int N, const int64_t *shape
         rp.map[a] = (const int32_t *)((const unsigned char *)p->kmeta.p + ml.map_off[a]);
         rp.F[a] = pl.tl[a].F; rp.V[a] = pl.tl[a].F; rp.ntiles[a] = 1; rp.Kd[a] = 1; rp.s[a] = 1; rp.O[a] = shape[a];
     }
-    rp.ws = (cx<R> *)p->ws.p; rp.H = pl.H; rp.Hp = pl.Hp; rp.rows_per_tile = pl.rows_per_tile; rp.tile_elems = pl.tile_elems;
-    st = fill_plan_dev<R>(p, pl.fl[N - 1], &rp.plan); if (st) return st;
-    if (!is_cx) { st = get_tw_r<R>(p, Fl, &rp.twr); if (st) return st; }
+    rp.ws = ws_a; rp.H = pl.H; rp.Hp = pl.Hp; rp.rows_per_tile = pl.rows_per_tile; rp.tile_elems = pl.tile_elems;
+    if (!last_global) {
+        st = fill_plan_dev<R>(p, pl.fl[N - 1], &rp.plan); if (st) return st;
+        if (!is_cx) { st = get_tw_r<R>(p, (int)Fl, &rp.twr); if (st) return st; }
+    }
     PermuteParams<R> pp; pp.n0 = N > 1 ? shape[0] : 1; pp.rest_rows = N > 1 ? pl.rows_per_tile / shape[0] : 1; pp.H = pl.H; pp.Hp = pl.Hp;
     const int64_t pgrid = std::min<int64_t>((int64_t)(spec_elems + 255) / 256, (int64_t)p->num_sms * 16 * kMaxGridMult);
     const double sb = (double)spec_bytes;
+    // strided axis a of the workspace: inner = Hp * prod F[b > a], outer = prod F[b < a]
+    auto col_axis = [&](int a, bool inv, cx<R> **cur, cx<R> **alt) -> int {
+        if (in_smem[a]) return run_col<R>(p, pl, a, inv ? 1 : 0, *cur, nullptr, 1, inv ? "fft_col_inv" : "fft_col_fwd", 2 * sb);
+        int64_t inner = pl.Hp, outer = 1;
+        for (int b = a + 1; b < N - 1; b++) inner *= shape[b];
+        for (int b = 0; b < a; b++) outer *= shape[b];
+        return run_global_axis<R>(p, shape[a], inner, outer, inv, cur, alt, inv ? "fft_gpass_inv" : "fft_gpass_fwd");
+    };
+    cx<R> *cur = ws_a, *alt = ws_b;
     if (!inverse) {
-        rp.x = dev_in;
-        st = run_row<R>(p, 0, rp, 0, "fft_row_fwd", (double)real_bytes + sb); if (st) return st;
-        for (int a = N - 2; a >= 0; a--) { st = run_col<R>(p, pl, a, 0, rp.ws, nullptr, 1, "fft_col_fwd", 2 * sb); if (st) return st; }
-        pp.src = rp.ws; pp.dst = (cx<R> *)dev_out; pp.to_rotated = 1;
+        if (!last_global) {
+            rp.x = dev_in;
+            st = run_row<R>(p, 0, rp, 0, "fft_row_fwd", (double)real_bytes + sb); if (st) return st;
+        } else {
+            cx<R> *rc = row_a, *ra = row_b;
+            st = run_gmove<R>(p, is_cx ? 1 : 0, dev_in, rc, rows, Fl, Fl, Fl, Fl, (R)0, "fft_row_pack"); if (st) return st;
+            st = run_global_axis<R>(p, Fl, 1, rows, false, &rc, &ra, "fft_gpass_fwd"); if (st) return st;
+            st = run_gmove<R>(p, 1, rc, ws_a, rows, Fl, Fl, pl.Hp, pl.H, (R)0, "fft_row_pack"); if (st) return st;
+        }
+        for (int a = N - 2; a >= 0; a--) { st = col_axis(a, false, &cur, &alt); if (st) return st; }
+        pp.src = cur; pp.dst = (cx<R> *)dev_out; pp.to_rotated = 1;
         st = launch<PermuteBody<R>, PermuteParams<R>>(p->lc(), "fft_layout_rotate", 2 * sb, pgrid, 256, 0, pp); if (st) return st;
     } else {
-        pp.src = (const cx<R> *)dev_in; pp.dst = rp.ws; pp.to_rotated = 0;
+        pp.src = (const cx<R> *)dev_in; pp.dst = ws_a; pp.to_rotated = 0;
         st = launch<PermuteBody<R>, PermuteParams<R>>(p->lc(), "fft_layout_rotate", 2 * sb, pgrid, 256, 0, pp); if (st) return st;
-        for (int a = 0; a <= N - 2; a++) { st = run_col<R>(p, pl, a, 1, rp.ws, nullptr, 1, "fft_col_inv", 2 * sb); if (st) return st; }
-        rp.out = dev_out; rp.scale = (R)(1.0L / (long double)total);            // real.rs:278-279, complex.rs:141-142
-        st = run_row<R>(p, 1, rp, pl.rows_per_tile, "fft_row_inv", (double)real_bytes + sb); if (st) return st;
+        for (int a = 0; a <= N - 2; a++) { st = col_axis(a, true, &cur, &alt); if (st) return st; }
+        const R scale = (R)(1.0L / (long double)total);                          // real.rs:278-279, complex.rs:141-142
+        if (!last_global) {
+            rp.ws = cur; rp.out = dev_out; rp.scale = scale;
+            st = run_row<R>(p, 1, rp, pl.rows_per_tile, "fft_row_inv", (double)real_bytes + sb); if (st) return st;
+        } else {
+            cx<R> *rc = row_a, *ra = row_b;
+            st = run_gmove<R>(p, is_cx ? 1 : 2, cur, rc, rows, Fl, pl.Hp, Fl, pl.H, (R)0, "fft_row_pack"); if (st) return st;
+            st = run_global_axis<R>(p, Fl, 1, rows, true, &rc, &ra, "fft_gpass_inv"); if (st) return st;
+            st = run_gmove<R>(p, is_cx ? 4 : 3, rc, dev_out, rows, Fl, Fl, Fl, Fl, scale, "fft_row_pack"); if (st) return st;
+        }
     }
     if (memory == NDCONV_MEM_HOST) {
         st = be_d2h(out, dev_out, out_bytes, p->stream); if (st) return st;

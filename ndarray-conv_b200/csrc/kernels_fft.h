@@ -520,6 +520,110 @@ template <class R> struct ColBody {
     }
 };
 
+// ---- global-memory Stockham pass (public processors only: axes outside the shared-memory envelope) ---------------
+// rustfft takes any length (real.rs:40,62; complex.rs:56); the shared-memory bodies above take {2,3,5,7}-smooth lengths
+// of at most one tile.  Everything else -- longer axes, odd real axes, prime factors above 7 -- runs as out-of-place
+// autosort Stockham passes through HBM, one launch per radix: element (o, i, c) of the transformed axis lives at
+// (o * n + i) * inner + c.  Radices 2..16 are register butterflies (one thread per butterfly); any other prime factor r
+// is evaluated as an r-term sum per output (one thread per output, O(n * r) for the pass) with the twiddle and the
+// radix-r root taken from the one table exp(-2 pi i j / n).
+template <class R> struct GPassParams {
+    const cx<R> *in;
+    cx<R> *out;
+    int64_t n, m, Ns;           // axis length, n / radix, product of the earlier radices
+    int radix;
+    int64_t inner, outer;
+    const cx<R> *tw;            // tw[j] = exp(-2 pi i j / n), j in [0, n)
+    int inv;
+    int64_t nwork;              // register radix: outer * m * inner butterflies; generic: outer * n * inner outputs
+};
+
+template <class R, int RDX> HD void gpass_butterfly(const GPassParams<R> &p, int64_t o, int64_t j, int64_t cc)
+{
+    const int64_t k = j % p.Ns, jq = j / p.Ns, step = p.n / (p.Ns * RDX);
+    const cx<R> *src = p.in + (o * p.n) * p.inner + cc;
+    cx<R> v[RDX];
+    for (int t = 0; t < RDX; t++) v[t] = src[(j + t * p.m) * p.inner];
+    if (p.Ns > 1) {
+        for (int t = 1; t < RDX; t++) {
+            const cx<R> w = p.tw[t * k * step];
+            v[t] = p.inv ? cmulc(v[t], w) : cmul(v[t], w);
+        }
+    }
+    dft<R, RDX>(v, p.inv != 0);
+    cx<R> *dst = p.out + (o * p.n) * p.inner + cc;
+    const int64_t j0 = jq * p.Ns * RDX + k;
+    for (int t = 0; t < RDX; t++) dst[(j0 + t * p.Ns) * p.inner] = v[t];
+}
+
+template <class R> struct GPassBody {
+    static HD void run(const BlockCtx &c, const GPassParams<R> &p)
+    {
+        const int r = p.radix;
+        const bool reg = r == 2 || r == 3 || r == 4 || r == 5 || r == 7 || r == 8 || r == 16;
+        for (int64_t e = c.bid * c.nt + c.tid; e < p.nwork; e += c.nb * c.nt) {
+            const int64_t cc = e % p.inner, rest = e / p.inner;
+            if (reg) {
+                const int64_t j = rest % p.m, o = rest / p.m;
+                switch (r) {
+                case 2: gpass_butterfly<R, 2>(p, o, j, cc); break;
+                case 3: gpass_butterfly<R, 3>(p, o, j, cc); break;
+                case 4: gpass_butterfly<R, 4>(p, o, j, cc); break;
+                case 5: gpass_butterfly<R, 5>(p, o, j, cc); break;
+                case 7: gpass_butterfly<R, 7>(p, o, j, cc); break;
+                case 8: gpass_butterfly<R, 8>(p, o, j, cc); break;
+                default: gpass_butterfly<R, 16>(p, o, j, cc); break;
+                }
+            } else {
+                // output (j, q): X = sum_t in[j + t m] * W_n^{t (k step + m q)}; the exponent advances by d modulo n
+                const int64_t i = rest % p.n, o = rest / p.n;
+                const int64_t q = i / p.m, j = i % p.m;
+                const int64_t k = j % p.Ns, jq = j / p.Ns, step = p.n / (p.Ns * r);
+                const int64_t d = (k * step + p.m * q) % p.n;
+                const cx<R> *src = p.in + (o * p.n + j) * p.inner + cc;
+                double are = 0.0, aim = 0.0;                   // r can be a long prime: sum in double for either element type
+                int64_t ex = 0;
+                for (int t = 0; t < r; t++) {
+                    const cx<R> x = src[(int64_t)t * p.m * p.inner];
+                    const cx<R> w = p.tw[ex];
+                    const double wr = (double)w.re, wi = p.inv ? -(double)w.im : (double)w.im;
+                    are += (double)x.re * wr - (double)x.im * wi;
+                    aim += (double)x.re * wi + (double)x.im * wr;
+                    ex += d; if (ex >= p.n) ex -= p.n;
+                }
+                p.out[(o * p.n + jq * p.Ns * r + k + q * p.Ns) * p.inner + cc] = cx<R>{(R)are, (R)aim};
+            }
+        }
+    }
+};
+
+// last-axis re-packing around the global passes: rows of `spitch` source elements -> rows of `dpitch` destination elements
+template <class R> struct GMoveParams {
+    const void *src;
+    void *dst;
+    int64_t rows, n, spitch, dpitch, H;
+    int mode;   // 0 real -> complex; 1 complex copy of H bins, zero up to dpitch; 2 Hermitian half (H = n/2+1 bins) -> n bins;
+                // 3 real part * scale -> real; 4 complex * scale -> complex
+    R scale;
+};
+template <class R> struct GMoveBody {
+    static HD void run(const BlockCtx &c, const GMoveParams<R> &p)
+    {
+        const int64_t total = p.rows * p.dpitch;
+        for (int64_t e = c.bid * c.nt + c.tid; e < total; e += c.nb * c.nt) {
+            const int64_t k = e % p.dpitch, row = e / p.dpitch;
+            const cx<R> zero = cx<R>{(R)0, (R)0};
+            if (p.mode == 0) ((cx<R> *)p.dst)[e] = cx<R>{((const R *)p.src)[row * p.spitch + k], (R)0};
+            else if (p.mode == 1) ((cx<R> *)p.dst)[e] = k < p.H ? ((const cx<R> *)p.src)[row * p.spitch + k] : zero;
+            else if (p.mode == 2) {
+                const cx<R> *s = (const cx<R> *)p.src + row * p.spitch;
+                ((cx<R> *)p.dst)[e] = k < p.H ? s[k] : cconj(s[p.n - k]);
+            } else if (p.mode == 3) ((R *)p.dst)[e] = ((const cx<R> *)p.src)[row * p.spitch + k].re * p.scale;
+            else { const cx<R> v = ((const cx<R> *)p.src)[row * p.spitch + k]; ((cx<R> *)p.dst)[e] = cx<R>{v.re * p.scale, v.im * p.scale}; }
+        }
+    }
+};
+
 // ---- spectrum layout of the public processors -------------------------------------------------------
 // natural [n0][rest (pitch-padded last axis)]  <->  rotated [rest (dense)][n0]: "axis 0 moves to the end".
 template <class R> struct PermuteParams {

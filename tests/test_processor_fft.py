@@ -15,6 +15,10 @@ def expected_spectrum(x):
 
 
 SHAPES = [(16,), (30,), (6, 10), (12, 40), (4, 6, 8), (5, 7, 12), (3, 4, 5, 6)]
+# outside the shared-memory envelope -> global-memory Stockham passes: odd real axes, prime factors above 7 (rustfft takes any
+# length: real.rs:40,62, complex.rs:56), axes longer than one shared-memory transform
+ANY_LENGTH_SHAPES = [(1,), (7,), (22,), (13,), (97,), (1, 1), (11, 13), (6, 15), (26, 34), (3, 5, 7), (2, 11, 9), (17, 4, 6), (3, 2, 5, 3),
+                     (1100, 6), (3, 1056, 4), (2, 9000), (8400,)]
 
 
 @pytest.mark.parametrize("shape", SHAPES, ids=str)
@@ -25,8 +29,6 @@ def test_forward_layout_and_roundtrip(ndc, shape, dtype):
     x = rng.standard_normal(shape).astype(dtype)
     if np.iscomplexobj(x):
         x = x + 1j * rng.standard_normal(shape).astype(dtype)
-    elif shape[-1] % 2:
-        pytest.skip("odd real last axis is outside this build's envelope")
     proc = pkg.get_fft_processor(0, lib)
     spec = proc.forward(x)
     ref = expected_spectrum(x)
@@ -39,15 +41,24 @@ def test_forward_layout_and_roundtrip(ndc, shape, dtype):
     proc.close()
 
 
-def test_unsupported_lengths_are_reported(ndc):
+@pytest.mark.parametrize("shape", ANY_LENGTH_SHAPES, ids=str)
+@pytest.mark.parametrize("dtype", [np.float32, np.float64, np.complex64, np.complex128], ids=["f32", "f64", "c32", "c64"])
+def test_any_length(ndc, shape, dtype):
+    test_forward_layout_and_roundtrip(ndc, shape, dtype)
+
+
+def test_spectrum_of_other_origin_len(ndc):
+    """real.rs:41,108: backward takes the real-space last-axis length from the processor (rp_origin_len), so the same half
+    spectrum width (6 bins) inverts to 10 or to 11 samples depending on the shape handed over."""
     pkg, lib = ndc
     proc = pkg.get_fft_processor(0, lib)
-    with pytest.raises(pkg.NdConvError) as e:
-        proc.forward(np.zeros(22, np.float32))      # 11 is not {2,3,5,7}-smooth
-    assert e.value.status == pkg.ERR_UNSUPPORTED
-    with pytest.raises(pkg.NdConvError) as e:
-        proc.forward(np.zeros((2000, 4), np.float32))   # strided axis longer than one shared-memory transform
-    assert e.value.status == pkg.ERR_UNSUPPORTED
+    rng = np.random.default_rng(3)
+    for n in (10, 11):
+        x = rng.standard_normal((4, n))
+        spec = np.moveaxis(np.fft.rfftn(x), 0, -1)
+        assert spec.shape == (6, 4)
+        back = proc.backward(spec, shape=(4, n), dtype=np.float64)
+        assert np.max(np.abs(back - x)) <= 1e-10
     proc.close()
 
 
@@ -63,4 +74,25 @@ def test_reference_roundtrip_200x5000(pkg, cuda_lib):
     assert np.max(np.abs(spec - ref)) <= 8 * np.finfo(np.float32).eps * np.log2(x.size) * np.max(np.abs(ref))
     back = proc.backward(spec)
     assert np.max(np.abs(back - x)) < 1e-6
+    proc.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape,dtype", [((2048, 2048), np.float32), ((65536,), np.float32), ((4099,), np.complex64), ((3000, 1001), np.float64),
+                                          ((6, 1500, 130), np.complex64)], ids=str)
+def test_global_passes_at_size(pkg, cuda_lib, shape, dtype):
+    """axes outside the shared-memory envelope at sizes that fill the device: 2048-point strided axis, a 65536-point row,
+    a prime length, an odd real axis next to a 3000-point strided axis, a 1500-point middle axis"""
+    rng = np.random.default_rng(4)
+    x = rng.standard_normal(shape).astype(dtype)
+    if np.iscomplexobj(x):
+        x = x + 1j * rng.standard_normal(shape).astype(dtype)
+    proc = pkg.get_fft_processor(0, cuda_lib)
+    spec = proc.forward(x)
+    ref = expected_spectrum(x)
+    assert spec.shape == ref.shape
+    eps = np.finfo(np.float32 if x.dtype in (np.float32, np.complex64) else np.float64).eps
+    assert np.max(np.abs(spec - ref)) <= 8 * eps * np.log2(x.size) * np.max(np.abs(ref))
+    back = proc.backward(spec)
+    assert np.max(np.abs(back - x)) <= (1e-6 if eps > 1e-10 else 1e-10) * max(1.0, np.max(np.abs(x))) * 4
     proc.close()
