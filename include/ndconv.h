@@ -158,6 +158,13 @@ int ndconv_conv_direct(ndconv_processor *p, const ndconv_problem *problem, void 
 int ndconv_conv_fft(ndconv_processor *p, const ndconv_problem *problem, void *out);
 /* ConvFFTExt::conv_fft_par, src/conv_fft/mod.rs:414-423: same GPU call (the parallelism is the device's). */
 int ndconv_conv_fft_par(ndconv_processor *p, const ndconv_problem *problem, void *out);
+/* conv_fft_par with more than one GPU configured: the reference's rayon path spreads one convolution over the
+ * host's cores (src/conv_fft/mod.rs:242-261); here one HOST-resident convolution is spread over `n_processors` handles (one
+ * per GPU, any mix of devices): output rows of axis 0 are cut into one contiguous overlap-save slab per handle
+ * (ndconv_slab_plan) and every handle runs H2D | kernels | D2H on its rows from its own host thread, over its own PCIe link,
+ * with no data-path collective; all handles write into the one `out` array.  Problems too small to pipeline run on
+ * processors[0] alone.  Results are those of ndconv_conv_fft up to rounding (slabs may pick other tile lengths). */
+int ndconv_conv_fft_sharded(ndconv_processor *const *processors, int n_processors, const ndconv_problem *problem, void *out);
 
 /* ---- Processor::{forward, backward}, src/conv_fft/processor/mod.rs:91-118 (real.rs:24-281, complex.rs:33-145) --------------
  * N-d FFT with the reference's spectrum layout: `shape` is always the shape of the REAL-SPACE array

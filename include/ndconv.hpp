@@ -253,4 +253,14 @@ Array<T, N> conv_fft_par(const Array<T, N> &x, const K &kernel, const ConvMode<N
     return run<T, N>(pr, NDCONV_PATH_FFT, [&](void *o) { return ndconv_conv_fft_par(nullptr, &pr, o); });
 }
 
+// conv_fft_par with several GPUs configured (ndconv_conv_fft_sharded): one axis-0 slab of output rows per processor
+template <class T, size_t N, class K>
+Array<T, N> conv_fft_par(const Array<T, N> &x, const K &kernel, const ConvMode<N> &mode, const PaddingMode<N, T> &pm, const std::vector<FftProcessor *> &procs)
+{
+    const auto pr = lower(x.view(), into_kernel_with_dilation(kernel), mode, pm);
+    std::vector<ndconv_processor *> raw;
+    for (FftProcessor *p : procs) raw.push_back(p->raw());
+    return run<T, N>(pr, NDCONV_PATH_FFT, [&](void *o) { return ndconv_conv_fft_sharded(raw.data(), (int)raw.size(), &pr, o); });
+}
+
 }  // namespace ndconv

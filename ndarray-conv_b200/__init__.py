@@ -83,7 +83,7 @@ EXPORTED_SYMBOLS = [
     "ndconv_border_index_map", "ndconv_processor_create", "ndconv_processor_destroy", "ndconv_processor_set_stream",
     "ndconv_processor_synchronize", "ndconv_processor_launch_count", "ndconv_processor_workspace_bytes",
     "ndconv_processor_set_profiling", "ndconv_processor_get_profile",
-    "ndconv_conv_direct", "ndconv_conv_fft", "ndconv_conv_fft_par", "ndconv_fft_forward", "ndconv_fft_backward",
+    "ndconv_conv_direct", "ndconv_conv_fft", "ndconv_conv_fft_par", "ndconv_conv_fft_sharded", "ndconv_fft_forward", "ndconv_fft_backward",
     "ndconv_slab_plan", "ndconv_host_alloc", "ndconv_host_free",
 ]
 
@@ -120,6 +120,7 @@ class Library:
         c.ndconv_processor_get_profile.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
         for name in ("ndconv_conv_direct", "ndconv_conv_fft", "ndconv_conv_fft_par"):
             getattr(c, name).argtypes = [ctypes.c_void_p, ctypes.POINTER(_Problem), ctypes.c_void_p]
+        c.ndconv_conv_fft_sharded.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, ctypes.POINTER(_Problem), ctypes.c_void_p]
         for name in ("ndconv_fft_forward", "ndconv_fft_backward"):
             getattr(c, name).argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
         c.ndconv_slab_plan.argtypes = [ctypes.POINTER(_Problem), ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(_Slab)]
@@ -446,6 +447,23 @@ def conv_fft_with_processor(x, kernel, conv_mode, padding_mode, processor: Proce
 def conv_fft_par(x, kernel, conv_mode=ConvMode.Same, padding_mode=PaddingMode.Zeros, lib=None):
     """ConvFFTExt::conv_fft_par (src/conv_fft/mod.rs:414-423): same GPU call -- the parallelism is the device's."""
     return _run_host("ndconv_conv_fft_par", PATH_FFT, x, kernel, conv_mode, padding_mode, None, lib)
+
+
+def conv_fft_sharded(x, kernel, conv_mode, padding_mode, processors, out=None):
+    """conv_fft_par over several GPUs of this process (ndconv_conv_fft_sharded): one axis-0 slab of output rows per processor,
+    each on its own host thread and PCIe link.  `x` / `out` should be pinned (ndconv_host_alloc) for full-rate copies."""
+    lib = processors[0].lib
+    x = np.asarray(x)
+    kwd = _into_kwd(kernel)
+    pr, keep = make_problem(x.shape, [s // x.itemsize for s in x.strides], x.ctypes.data, x.dtype, kwd, conv_mode, padding_mode, MEM_HOST, lib)
+    shp = out_shape(pr, PATH_FFT, lib)
+    if out is None:
+        out = np.empty(shp, x.dtype)
+    assert tuple(out.shape) == tuple(shp) and out.dtype == x.dtype and out.flags.c_contiguous
+    handles = (ctypes.c_void_p * len(processors))(*[p.handle for p in processors])
+    lib.check(lib.c.ndconv_conv_fft_sharded(handles, len(processors), ctypes.byref(pr), out.ctypes.data))
+    del keep
+    return out
 
 
 def conv_device(entry, processor: Processor, x_ptr, x_shape, x_strides_elems, dtype, kernel, conv_mode, padding_mode, out_ptr, explicit=None):

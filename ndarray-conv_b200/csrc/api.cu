@@ -11,7 +11,9 @@
 #include <limits>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "host_logic.h"
@@ -42,6 +44,18 @@ typedef cudaStream_t stream_t;
         }                                                                                                \
     } while (0)
 
+// cudaFuncSetAttribute configures a kernel on the CURRENT device only: remember, per call site, which devices have been
+// configured (a process may hold processors on several GPUs, and ndconv_conv_fft_sharded drives them from one host thread each)
+#define NDC_ONCE_PER_DEVICE(...)                                                                         \
+    do {                                                                                                 \
+        static std::mutex mu_;                                                                           \
+        static uint64_t done_ = 0;                                                                       \
+        int dev_ = 0;                                                                                    \
+        cudaGetDevice(&dev_);                                                                            \
+        std::lock_guard<std::mutex> lk_(mu_);                                                            \
+        if (!((done_ >> (dev_ & 63)) & 1)) { __VA_ARGS__; done_ |= 1ull << (dev_ & 63); }                \
+    } while (0)
+
 template <class Body, class Params> __global__ void __launch_bounds__(512) kentry(const __grid_constant__ Params p)
 {
     extern __shared__ __align__(16) unsigned char ndc_smem[];
@@ -62,11 +76,7 @@ struct LaunchCtx { stream_t st; int64_t *counter; Profiler *prof; };
 template <class Body, class Params>
 static int launch(const LaunchCtx &lc, const char *name, double alg_bytes, int64_t grid, int block, size_t smem, const Params &p)
 {
-    static bool attr_set = false;
-    if (!attr_set) {
-        CU_CHECK(cudaFuncSetAttribute(kentry<Body, Params>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_set = true;
-    }
+    NDC_ONCE_PER_DEVICE(CU_CHECK(cudaFuncSetAttribute(kentry<Body, Params>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)));
     if (grid < 1) grid = 1;
     ProfRec rec;
     const bool prof = lc.prof && lc.prof->on;
@@ -584,8 +594,7 @@ static bool value_is_zero(const ndconv_border &b, int es)
 template <class T>
 static int launch_direct_tile(ndconv_processor *p, const CUtensorMap &tm, const tile::TileParams &tp, int64_t grid, size_t smem, double alg_bytes)
 {
-    static bool attr_set = false;
-    if (!attr_set) { CU_CHECK(cudaFuncSetAttribute(tile::direct_tile_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr_set = true; }
+    NDC_ONCE_PER_DEVICE(CU_CHECK(cudaFuncSetAttribute(tile::direct_tile_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)));
     const stream_t stm = p->stream;
     return launch_raw(p->lc(), tp.use_tma ? "direct_conv_tile_tma" : "direct_conv_tile", alg_bytes,
                       [&] { tile::direct_tile_kernel<T><<<(unsigned)grid, tile::kThreads, smem, stm>>>(tm, tp); });
@@ -909,23 +918,15 @@ static int get_kernel_spectrum(ndconv_processor *p, const ndconv_problem *pr, co
 // sm_100a fast path: real f32, rank 2 / 3, power-of-two overlap-save tiles (kernels_fft_fast.cuh)
 template <int T, int N> static void launch_row_n(bool inverse, const fast::RowParams &rp, int grid, stream_t stm)
 {
-    static bool attr = false;
-    if (!attr) {
-        cudaFuncSetAttribute(fast::row_fwd<T, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, fast::RowCfg<T>::smem);
-        cudaFuncSetAttribute(fast::row_inv<T, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, fast::RowCfg<T>::smem);
-        attr = true;
-    }
+    NDC_ONCE_PER_DEVICE(cudaFuncSetAttribute(fast::row_fwd<T, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, fast::RowCfg<T>::smem);
+                        cudaFuncSetAttribute(fast::row_inv<T, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, fast::RowCfg<T>::smem));
     if (inverse) fast::row_inv<T, N><<<grid, 128, fast::RowCfg<T>::smem, stm>>>(rp);
     else fast::row_fwd<T, N><<<grid, 128, fast::RowCfg<T>::smem, stm>>>(rp);
 }
 template <int T, int N> static void launch_row_cx_n(bool inverse, const fast::RowParams &rp, int grid, stream_t stm)
 {
-    static bool attr = false;
-    if (!attr) {
-        cudaFuncSetAttribute(fast::row_fwd_c<T, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, fast::RowCxCfg<T>::smem);
-        cudaFuncSetAttribute(fast::row_inv_c<T, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, fast::RowCxCfg<T>::smem);
-        attr = true;
-    }
+    NDC_ONCE_PER_DEVICE(cudaFuncSetAttribute(fast::row_fwd_c<T, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, fast::RowCxCfg<T>::smem);
+                        cudaFuncSetAttribute(fast::row_inv_c<T, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, fast::RowCxCfg<T>::smem));
     if (inverse) fast::row_inv_c<T, N><<<grid, 128, fast::RowCxCfg<T>::smem, stm>>>(rp);
     else fast::row_fwd_c<T, N><<<grid, 128, fast::RowCxCfg<T>::smem, stm>>>(rp);
 }
@@ -936,14 +937,12 @@ template <int T> static void launch_row_cx(bool inverse, const fast::RowParams &
 }
 template <int T> static void launch_row1d_cx(const fast::RowParams &rp, int grid, stream_t stm)
 {
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(fast::row1d_c<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, fast::Row1dCxCfg<T>::smem); attr = true; }
+    NDC_ONCE_PER_DEVICE(cudaFuncSetAttribute(fast::row1d_c<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, fast::Row1dCxCfg<T>::smem));
     fast::row1d_c<T><<<grid, 128, fast::Row1dCxCfg<T>::smem, stm>>>(rp);
 }
 template <int T> static void launch_row1d(const fast::RowParams &rp, int grid, stream_t stm)
 {
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(fast::row1d<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, fast::Row1dCfg<T>::smem); attr = true; }
+    NDC_ONCE_PER_DEVICE(cudaFuncSetAttribute(fast::row1d<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, fast::Row1dCfg<T>::smem));
     fast::row1d<T><<<grid, 128, fast::Row1dCfg<T>::smem, stm>>>(rp);
 }
 template <int T> static void launch_row(bool inverse, const fast::RowParams &rp, int grid, stream_t stm)
@@ -954,8 +953,7 @@ template <int T> static void launch_row(bool inverse, const fast::RowParams &rp,
 template <int E, int Tc> static void launch_col_t(const fast::ColParams &cp, int num_sms, stream_t stm)
 {
     using C = fast::ColCfg<E, Tc>;
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(fast::col_pass<E, Tc>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::smem); attr = true; }
+    NDC_ONCE_PER_DEVICE(cudaFuncSetAttribute(fast::col_pass<E, Tc>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::smem));
     const int per_sm = std::max(1, std::min(16, (int)((200 * 1024) / C::smem)));
     const int grid = (int)std::min<int64_t>(cp.nwork, (int64_t)num_sms * std::max(C::min_blocks, std::min(per_sm, 2048 / C::threads)));
     fast::col_pass<E, Tc><<<grid, C::threads, C::smem, stm>>>(cp);
@@ -1238,8 +1236,14 @@ static bool pipeline_eligible(const ndconv_problem *pr, const Geom &g)
     return bytes >= kPipelineMinBytes && g.O[0] >= 4;
 }
 
-static int conv_fft_host_pipelined(ndconv_processor *p, const ndconv_problem *pr, const Geom &g, const std::vector<int32_t> &map0, void *out)
+// [o_lo, o_hi): the output rows of axis 0 this call produces (the whole axis for a single-GPU call, one slab of it per GPU in
+// ndconv_conv_fft_sharded); `out` is always the base of the full output array
+static int conv_fft_host_pipelined(ndconv_processor *p, const ndconv_problem *pr, const Geom &g, const std::vector<int32_t> &map0, void *out,
+                                   int64_t o_lo = 0, int64_t o_hi = -1)
 {
+    if (o_hi < 0) o_hi = g.O[0];
+    if (o_hi <= o_lo) return NDCONV_OK;
+    const int64_t O0 = o_hi - o_lo;
     const int N = g.ndim;
     int st;
     if (!p->h2d_stream) {
@@ -1265,8 +1269,8 @@ static int conv_fft_host_pipelined(ndconv_processor *p, const ndconv_problem *pr
         for (int F = fullpl.tl[0].F / 2; F >= 64 && rows < V0; F /= 2) { const int64_t v = (F - g.Kd[0] + 1) / g.s[0]; if (v >= 1 && 2 * (F - g.Kd[0] + 1) >= F) V0 = v; else break; }
     }
     rows = std::max<int64_t>(V0, rows / V0 * V0);
-    if (rows >= g.O[0]) rows = std::max<int64_t>(1, (g.O[0] + 1) / 2);
-    const int64_t nslab = (g.O[0] + rows - 1) / rows;
+    if (rows >= O0) rows = std::max<int64_t>(1, (O0 + 1) / 2);
+    const int64_t nslab = (O0 + rows - 1) / rows;
     const int64_t max_in_rows = (rows - 1) * g.s[0] + g.Kd[0];
     for (int b = 0; b < 2; b++) {
         st = p->pipe_in[b].reserve((size_t)max_in_rows * in_row_bytes); if (st) return st;
@@ -1288,7 +1292,7 @@ static int conv_fft_host_pipelined(ndconv_processor *p, const ndconv_problem *pr
     int64_t prev_pb = 0, prev_pe = 0;
     for (int64_t sidx = 0; sidx < nslab; sidx++) {
         const int b = (int)(sidx & 1);
-        const int64_t ob = sidx * rows, oe = std::min<int64_t>(g.O[0], ob + rows);
+        const int64_t ob = o_lo + sidx * rows, oe = std::min<int64_t>(o_hi, ob + rows);
         const int64_t pb = ob * g.s[0], pe = (oe - 1) * g.s[0] + g.Kd[0];       // padded rows read by this slab
         // ---- H2D: materialise padded rows [pb, pe) of axis 0 ----
         if (sidx >= 2) CU_CHECK(cudaStreamWaitEvent(p->h2d_stream, p->ev_comp[b], 0));   // kernels of slab s-2 have consumed pipe_in[b]
@@ -1760,6 +1764,43 @@ int ndconv_slab_plan(const ndconv_problem *problem, int path, int n_slabs, int s
     Geom g; std::vector<int32_t> maps[NDC_MAX_DIM];
     int st = check_problem(problem, path, &g, maps); if (st) return st;
     return slab_plan(g, n_slabs, slab, out);
+}
+
+// One host-resident convolution over several GPUs of this process (conv_fft_par with more than one device
+// configured): the output rows of axis 0 are split into one contiguous slab per handle (slab_plan), and every handle runs the
+// pipelined host path on its own rows from its own host thread -- H2D | kernels | D2H per GPU, each over its own PCIe link, no
+// data-path collective.  Handles may live on the same device (the rows are then interleaved on that device's streams).
+int ndconv_conv_fft_sharded(ndconv_processor *const *handles, int n_handles, const ndconv_problem *problem, void *out)
+{
+    if (!handles || n_handles < 1) { set_error("conv_fft_sharded: no processors"); return NDCONV_ERR_BAD_ARG; }
+    for (int i = 0; i < n_handles; i++) if (!handles[i]) { set_error("conv_fft_sharded: null processor"); return NDCONV_ERR_BAD_ARG; }
+    if (problem && problem->memory != NDCONV_MEM_HOST) { set_error("conv_fft_sharded: the problem must be host-resident (device-resident slabs: one call per rank + halo exchange)"); return NDCONV_ERR_BAD_ARG; }
+#ifdef NDCONV_CUDA
+    if (n_handles > 1 && problem && !kernel_exceeds_fft_tiles(problem)) {
+        Geom g; std::vector<int32_t> maps[NDC_MAX_DIM];
+        int st = check_problem(problem, NDCONV_PATH_FFT, &g, maps); if (st) return st;
+        if (!out) { set_error("null output pointer"); return NDCONV_ERR_BAD_ARG; }
+        if (pipeline_eligible(problem, g) && g.O[0] >= 4 * (int64_t)n_handles) {
+            std::vector<int> status((size_t)n_handles, NDCONV_OK);
+            std::vector<std::string> message((size_t)n_handles);
+            std::vector<std::thread> workers;
+            for (int i = 0; i < n_handles; i++) {
+                workers.emplace_back([&, i]() {
+                    ndconv_slab sl;
+                    int s2 = slab_plan(g, n_handles, i, &sl);
+                    if (!s2) s2 = set_device(handles[i]);
+                    if (!s2) s2 = conv_fft_host_pipelined(handles[i], problem, g, maps[0], out, sl.out_begin, sl.out_end);
+                    status[(size_t)i] = s2;
+                    if (s2) message[(size_t)i] = get_error();       // the error string is thread-local
+                });
+            }
+            for (auto &w : workers) w.join();
+            for (int i = 0; i < n_handles; i++) if (status[(size_t)i]) { set_error(message[(size_t)i]); return status[(size_t)i]; }
+            return NDCONV_OK;
+        }
+    }
+#endif
+    return conv_fft_impl(handles[0], problem, out);
 }
 
 void *ndconv_host_alloc(size_t bytes)

@@ -153,6 +153,11 @@ static void device_tests()
             for (size_t i = 0; i < serial.len(); i++) { CHECK(std::fabs(serial.data[i] - par.data[i]) < 1e-4f); CHECK(std::fabs(serial.data[i] - wp.data[i]) < 1e-4f); }
         }
         CHECK(proc.launch_count() > 0);
+        // several processors configured: ndconv_conv_fft_sharded (a problem this small runs on the first one)
+        auto proc2 = get_fft_processor();
+        auto multi = conv_fft_par(arr, ker, ConvMode<2>::Same(), PaddingMode<2, float>::Zeros(), std::vector<FftProcessor *>{&proc, &proc2});
+        auto serial = conv_fft(arr, ker, ConvMode<2>::Same(), PaddingMode<2, float>::Zeros());
+        for (size_t i = 0; i < serial.len(); i++) CHECK(std::fabs(serial.data[i] - multi.data[i]) < 1e-4f);
     });
     run_test("processor::real::round_trip_2d (forward o backward = id, rotated layout [n1/2+1, n0])", [] {
         Array<double, 2> x({6, 10});
