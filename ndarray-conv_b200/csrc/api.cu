@@ -1067,6 +1067,8 @@ static int conv_fft_fast(ndconv_processor *p, const ndconv_problem *pr, const Ge
         const cx<float> *twc = nullptr;
         int s2 = get_tw_c<float>(p, pl.tl[axis].F, &twc); if (s2) return s2;
         cp.tw = twc;
+        static const bool no_skip = getenv("NDCONV_COL_NO_SKIP") != nullptr;
+        cp.skip = (mode != 0 && !no_skip) ? (int)g.Kd[axis] - 1 : 0;          // the crop discards tile rows [0, Kd - 1): row_inv never reads them
         return launch_raw(p->lc(), name, bytes, [&] { launch_col(pl.tl[axis].F, cp, p->num_sms, stm); });
     };
     // launches of the tail part of an axis-0 split are profiled under their own names: per-launch figures of the main kernels stay

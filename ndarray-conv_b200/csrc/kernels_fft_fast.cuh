@@ -798,6 +798,7 @@ struct ColParams {
     int64_t outer, inner;   // the tile is [outer][F][inner] complex, inner % 8 == 0
     int64_t tile_elems, ntiles_total;
     int64_t nwork;          // ntiles_total * outer * inner / 8
+    int skip;               // modes 1 / 2: the first `skip` rows of the axis (= Kd - 1, the aliased head the crop discards) are not stored
 };
 
 template <int E, int Tc> struct ColCfg {
@@ -915,7 +916,7 @@ __global__ void __launch_bounds__(ColCfg<E, Tc>::threads, ColCfg<E, Tc>::min_blo
         if (w + gridDim.x < p.nwork) { nxt = decode(w + gridDim.x); prefetch(nxt); }
         pk::dft<true, E>(v);
 #pragma unroll
-        for (int j = 0; j < E; j++) st_pc(gt + (int64_t)(i + Tc * j) * p.inner, v[j]);
+        for (int j = 0; j < E; j++) if (i + Tc * j >= p.skip) st_pc(gt + (int64_t)(i + Tc * j) * p.inner, v[j]);
     }
 }
 
