@@ -597,7 +597,15 @@ static int launch_direct_tile(ndconv_processor *p, const CUtensorMap &tm, const 
     NDC_ONCE_PER_DEVICE(CU_CHECK(cudaFuncSetAttribute(tile::direct_tile_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)));
     const stream_t stm = p->stream;
     return launch_raw(p->lc(), tp.use_tma ? "direct_conv_tile_tma" : "direct_conv_tile", alg_bytes,
-                      [&] { tile::direct_tile_kernel<T><<<(unsigned)grid, tile::kThreads, smem, stm>>>(tm, tp); });
+                      [&] {
+                          static const bool no_pdl = getenv("NDCONV_DISABLE_PDL") != nullptr;
+                          cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
+                          cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(tile::kThreads); cfg.dynamicSmemBytes = smem; cfg.stream = stm;
+                          cudaLaunchAttribute at[1];
+                          at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
+                          cfg.attrs = at; cfg.numAttrs = no_pdl ? 0 : 1;
+                          cudaLaunchKernelEx(&cfg, tile::direct_tile_kernel<T>, tm, tp);
+                      });
 }
 
 // returns NDCONV_OK with *used = false when the problem is outside the tile kernel's envelope (caller falls back)
@@ -916,19 +924,28 @@ static int get_kernel_spectrum(ndconv_processor *p, const ndconv_problem *pr, co
 
 #ifdef NDCONV_CUDA
 // sm_100a fast path: real f32, rank 2 / 3, power-of-two overlap-save tiles (kernels_fft_fast.cuh)
+// every fast-path kernel is launched with programmatic stream serialization (see pdl_wait in kernels_fft_fast.cuh)
+template <class P> static void launch_pdl(void (*kernel)(const P), int grid, int block, size_t smem, stream_t stm, const P &prm)
+{
+    static const bool no_pdl = getenv("NDCONV_DISABLE_PDL") != nullptr;
+    cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = smem; cfg.stream = stm;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = no_pdl ? 0 : 1;
+    cudaLaunchKernelEx(&cfg, kernel, prm);
+}
 template <int T, int N> static void launch_row_n(bool inverse, const fast::RowParams &rp, int grid, stream_t stm)
 {
     NDC_ONCE_PER_DEVICE(cudaFuncSetAttribute(fast::row_fwd<T, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, fast::RowCfg<T>::smem);
                         cudaFuncSetAttribute(fast::row_inv<T, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, fast::RowCfg<T>::smem));
-    if (inverse) fast::row_inv<T, N><<<grid, 128, fast::RowCfg<T>::smem, stm>>>(rp);
-    else fast::row_fwd<T, N><<<grid, 128, fast::RowCfg<T>::smem, stm>>>(rp);
+    launch_pdl<fast::RowParams>(inverse ? fast::row_inv<T, N> : fast::row_fwd<T, N>, grid, 128, fast::RowCfg<T>::smem, stm, rp);
 }
 template <int T, int N> static void launch_row_cx_n(bool inverse, const fast::RowParams &rp, int grid, stream_t stm)
 {
     NDC_ONCE_PER_DEVICE(cudaFuncSetAttribute(fast::row_fwd_c<T, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, fast::RowCxCfg<T>::smem);
                         cudaFuncSetAttribute(fast::row_inv_c<T, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, fast::RowCxCfg<T>::smem));
-    if (inverse) fast::row_inv_c<T, N><<<grid, 128, fast::RowCxCfg<T>::smem, stm>>>(rp);
-    else fast::row_fwd_c<T, N><<<grid, 128, fast::RowCxCfg<T>::smem, stm>>>(rp);
+    launch_pdl<fast::RowParams>(inverse ? fast::row_inv_c<T, N> : fast::row_fwd_c<T, N>, grid, 128, fast::RowCxCfg<T>::smem, stm, rp);
 }
 template <int T> static void launch_row_cx(bool inverse, const fast::RowParams &rp, int grid, stream_t stm)
 {
@@ -938,12 +955,12 @@ template <int T> static void launch_row_cx(bool inverse, const fast::RowParams &
 template <int T> static void launch_row1d_cx(const fast::RowParams &rp, int grid, stream_t stm)
 {
     NDC_ONCE_PER_DEVICE(cudaFuncSetAttribute(fast::row1d_c<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, fast::Row1dCxCfg<T>::smem));
-    fast::row1d_c<T><<<grid, 128, fast::Row1dCxCfg<T>::smem, stm>>>(rp);
+    launch_pdl<fast::RowParams>(fast::row1d_c<T>, grid, 128, fast::Row1dCxCfg<T>::smem, stm, rp);
 }
 template <int T> static void launch_row1d(const fast::RowParams &rp, int grid, stream_t stm)
 {
     NDC_ONCE_PER_DEVICE(cudaFuncSetAttribute(fast::row1d<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, fast::Row1dCfg<T>::smem));
-    fast::row1d<T><<<grid, 128, fast::Row1dCfg<T>::smem, stm>>>(rp);
+    launch_pdl<fast::RowParams>(fast::row1d<T>, grid, 128, fast::Row1dCfg<T>::smem, stm, rp);
 }
 template <int T> static void launch_row(bool inverse, const fast::RowParams &rp, int grid, stream_t stm)
 {
@@ -956,7 +973,7 @@ template <int E, int Tc> static void launch_col_t(const fast::ColParams &cp, int
     NDC_ONCE_PER_DEVICE(cudaFuncSetAttribute(fast::col_pass<E, Tc>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::smem));
     const int per_sm = std::max(1, std::min(16, (int)((200 * 1024) / C::smem)));
     const int grid = (int)std::min<int64_t>(cp.nwork, (int64_t)num_sms * std::max(C::min_blocks, std::min(per_sm, 2048 / C::threads)));
-    fast::col_pass<E, Tc><<<grid, C::threads, C::smem, stm>>>(cp);
+    launch_pdl<fast::ColParams>(fast::col_pass<E, Tc>, grid, C::threads, C::smem, stm, cp);
 }
 static void launch_col(int F, const fast::ColParams &cp, int num_sms, stream_t stm)
 {

@@ -82,6 +82,9 @@ __device__ __forceinline__ void tap_loop(uint32_t tile_addr, const T *s_w, const
 template <class T>
 __global__ void __launch_bounds__(kThreads) direct_tile_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TileParams p)
 {
+    // programmatic dependent launch (see kernels_fft_fast.cuh): the next kernel of the stream may start now; this one stages
+    // its window maps (plan constants) and only then waits for its predecessors, before the first read of x / write of out
+    asm volatile("griddepcontrol.launch_dependents;");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     T *tile = reinterpret_cast<T *>(smem_raw);
     const int tile_bytes = (p.tile_elems * (int)sizeof(T) + 127) & ~127;
@@ -158,6 +161,7 @@ __global__ void __launch_bounds__(kThreads) direct_tile_kernel(const __grid_cons
         }
     };
 
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     if (tma_ok) {
         if (tid == 0) {
             const uint32_t mb = smem_u32(&mbar);

@@ -27,6 +27,14 @@
 namespace ndc {
 namespace fast {
 
+// Programmatic dependent launch: every kernel of the fast path lets the next kernel of the stream start early
+// (launch_dependents at the top) and itself waits for its predecessors only after its prologue -- the twiddle tables staged
+// into shared memory come from per-processor constants no kernel writes -- so launch latency and prologue of kernel n+1 overlap
+// the tail of kernel n.  Nothing a predecessor writes (workspace, output) or reads (a workspace the successor overwrites) is
+// touched before pdl_wait().  Launched without the attribute (NDCONV_DISABLE_PDL) both are no-ops.
+DEV void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+DEV void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 typedef cx<float> cf;
 typedef pk::pcf pc;              // the same 8 bytes as cf, held as one 64-bit register pair for FADD2 / FMUL2 / FFMA2 (packed_cf.cuh)
 constexpr int kPad = 8;          // extra columns per row: Nyquist + 7 zeros (keeps rows 64-byte aligned; 128-byte rows measured no faster)
@@ -122,6 +130,7 @@ template <int N> __device__ __forceinline__ RowSrcInfo resolve_fwd_row(const Row
 template <int T, int N>
 __global__ void __launch_bounds__(128, 4) row_fwd(const __grid_constant__ RowParams p)
 {
+    pdl_launch_dependents();
     constexpr int L = RowCfg<T>::L, M = RowCfg<T>::M, G = RowCfg<T>::G;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     pc *s_tw = reinterpret_cast<pc *>(smem_raw);          // s_tw[k1 * T + t] = W_L^{t k1}
@@ -132,6 +141,7 @@ __global__ void __launch_bounds__(128, 4) row_fwd(const __grid_constant__ RowPar
     for (int idx = threadIdx.x; idx < L; idx += blockDim.x) s_tw[idx] = ld_pc(p.tw + (idx / T) * (idx % T));
     for (int idx = threadIdx.x; idx < L / 2; idx += blockDim.x) { const cf w = p.twr[idx]; s_twr[idx] = pk::mk(0.5f * w.im, -0.5f * w.re); }
     __syncthreads();
+    pdl_wait();
     pc *sb = s_ex + warp * RowCfg<T>::wstride + g * RowCfg<T>::gstride;
     constexpr int al = N - 1;
     const int src_lane = g * T + ((T - t) % T);
@@ -265,6 +275,7 @@ template <int N> __device__ __forceinline__ RowInvInfo resolve_inv_row(const Row
 template <int T, int N>
 __global__ void __launch_bounds__(128, 4) row_inv(const __grid_constant__ RowParams p)
 {
+    pdl_launch_dependents();
     constexpr int L = RowCfg<T>::L, M = RowCfg<T>::M, G = RowCfg<T>::G;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     pc *s_tw = reinterpret_cast<pc *>(smem_raw);          // TRANSPOSED for the inverse flow: s_tw[i * 32 + k1] = W_L^{i k1} (k1 is the lane-dependent index)
@@ -275,6 +286,7 @@ __global__ void __launch_bounds__(128, 4) row_inv(const __grid_constant__ RowPar
     for (int idx = threadIdx.x; idx < L; idx += blockDim.x) s_tw[idx] = ld_pc(p.tw + (idx >> 5) * (idx & 31));
     for (int idx = threadIdx.x; idx < L / 2; idx += blockDim.x) { const cf w = p.twr[idx]; s_twr[idx] = pk::mk(w.im, w.re); }
     __syncthreads();
+    pdl_wait();
     pc *sb = s_ex + warp * RowCfg<T>::wstride + g * RowCfg<T>::gstride;
     ulonglong2 *sb4 = reinterpret_cast<ulonglong2 *>(s_ex + warp * RowCfg<T>::wstride) + g * (L / 2 + 1);  // staging: L/2 slots + the Nyquist column, linear
     constexpr int al = N - 1;
@@ -396,6 +408,7 @@ template <int T> struct RowCxCfg { static constexpr int L = 32 * T, smem = (L + 
 template <int T, int N>
 __global__ void __launch_bounds__(128, 4) row_fwd_c(const __grid_constant__ RowParams p)
 {
+    pdl_launch_dependents();
     constexpr int L = RowCfg<T>::L, M = RowCfg<T>::M, G = RowCfg<T>::G;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     pc *s_tw = reinterpret_cast<pc *>(smem_raw);          // s_tw[k1 * T + t] = W_L^{t k1}
@@ -404,6 +417,7 @@ __global__ void __launch_bounds__(128, 4) row_fwd_c(const __grid_constant__ RowP
     const int g = lane / T, t = lane % T;
     for (int idx = threadIdx.x; idx < L; idx += blockDim.x) s_tw[idx] = ld_pc(p.tw + (idx / T) * (idx % T));
     __syncthreads();
+    pdl_wait();
     pc *sb = s_ex + warp * RowCfg<T>::wstride + g * RowCfg<T>::gstride;
     constexpr int al = N - 1;
     const cf *xc = reinterpret_cast<const cf *>(p.x);
@@ -461,6 +475,7 @@ __global__ void __launch_bounds__(128, 4) row_fwd_c(const __grid_constant__ RowP
 template <int T, int N>
 __global__ void __launch_bounds__(128, 4) row_inv_c(const __grid_constant__ RowParams p)
 {
+    pdl_launch_dependents();
     constexpr int L = RowCfg<T>::L, M = RowCfg<T>::M, G = RowCfg<T>::G;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     pc *s_tw = reinterpret_cast<pc *>(smem_raw);          // transposed: s_tw[i * 32 + k1] = W_L^{i k1}
@@ -469,6 +484,7 @@ __global__ void __launch_bounds__(128, 4) row_inv_c(const __grid_constant__ RowP
     const int g = lane / T, t = lane % T;
     for (int idx = threadIdx.x; idx < L; idx += blockDim.x) s_tw[idx] = ld_pc(p.tw + (idx >> 5) * (idx & 31));
     __syncthreads();
+    pdl_wait();
     pc *sb = s_ex + warp * RowCfg<T>::wstride + g * RowCfg<T>::gstride;
     constexpr int al = N - 1;
     cf *outc = reinterpret_cast<cf *>(p.out);
@@ -520,6 +536,7 @@ template <int T> struct Row1dCfg {
 template <int T>
 __global__ void __launch_bounds__(128, 3) row1d(const __grid_constant__ RowParams p)
 {
+    pdl_launch_dependents();
     constexpr int L = RowCfg<T>::L, M = RowCfg<T>::M, G = RowCfg<T>::G;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     pc *s_twF = reinterpret_cast<pc *>(smem_raw);         // s_twF[k1 * T + t] = W_L^{t k1}
@@ -539,6 +556,7 @@ __global__ void __launch_bounds__(128, 3) row1d(const __grid_constant__ RowParam
         s_pre[idx] = pk::mk(w.im, w.re);
     }
     __syncthreads();
+    pdl_wait();
     pc *sb = s_ex + warp * RowCfg<T>::wstride + g * RowCfg<T>::gstride;
     const int src_lane = g * T + ((T - t) % T);
     const pc half = pk::mk(0.5f, 0.5f);
@@ -703,6 +721,7 @@ template <int T> struct Row1dCxCfg { static constexpr int L = 32 * T, smem = (L 
 template <int T>
 __global__ void __launch_bounds__(128, 4) row1d_c(const __grid_constant__ RowParams p)
 {
+    pdl_launch_dependents();
     constexpr int L = RowCfg<T>::L, M = RowCfg<T>::M, G = RowCfg<T>::G;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     pc *s_twF = reinterpret_cast<pc *>(smem_raw);         // s_twF[k1 * T + t] = W_L^{t k1}
@@ -715,6 +734,7 @@ __global__ void __launch_bounds__(128, 4) row1d_c(const __grid_constant__ RowPar
         s_twI[idx] = ld_pc(p.tw + (idx >> 5) * (idx & 31));
     }
     __syncthreads();
+    pdl_wait();
     pc *sb = s_ex + warp * RowCfg<T>::wstride + g * RowCfg<T>::gstride;
     const cf *xc = reinterpret_cast<const cf *>(p.x);
     cf *outc = reinterpret_cast<cf *>(p.out);
@@ -813,6 +833,7 @@ template <int E, int Tc> struct ColCfg {
 template <int E, int Tc>
 __global__ void __launch_bounds__(ColCfg<E, Tc>::threads, ColCfg<E, Tc>::min_blocks) col_pass(const __grid_constant__ ColParams p)
 {
+    pdl_launch_dependents();
     using C = ColCfg<E, Tc>;
     constexpr int F = C::F, Mc = C::Mc, pitch = C::pitch;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -842,6 +863,7 @@ __global__ void __launch_bounds__(ColCfg<E, Tc>::threads, ColCfg<E, Tc>::min_blo
         }
         cp_async_commit();
     };
+    pdl_wait();                                      // before the first access to the workspace (the table staging above reads constants)
     Item nxt; nxt.off = 0; nxt.rel = 0;
     if ((int64_t)blockIdx.x < p.nwork) { nxt = decode(blockIdx.x); prefetch(nxt); }
     for (int64_t w = blockIdx.x; w < p.nwork; w += gridDim.x) {
