@@ -140,7 +140,9 @@ def test_workspace_budget_stripes(pkg, cuda_lib):
     )
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     outs, ws = [], []
-    for tag, env in (("full", {"NDCONV_DISABLE_SPLIT": "1"}), ("striped", {"NDCONV_WS_BUDGET_MB": "20"})):
+    # NDCONV_TILE_SLACK=-1: a stripe of this (deliberately tiny) array would count as a small problem and pick shorter tiles than
+    # the whole; real stripes (workspace over 24 GB) never do
+    for tag, env in (("full", {"NDCONV_DISABLE_SPLIT": "1", "NDCONV_TILE_SLACK": "-1"}), ("striped", {"NDCONV_WS_BUDGET_MB": "20", "NDCONV_TILE_SLACK": "-1"})):
         path = f"/tmp/ndconv_ws_{tag}.npy"
         r = subprocess.run([sys.executable, "-c", code, path], check=True, cwd=root, env={**os.environ, **env}, capture_output=True, text=True)
         outs.append(np.load(path))
