@@ -390,11 +390,12 @@ static int make_plan(const Geom &g, FftPlan *pl)
         if (pl->fast) {
             static const int menu_last[4] = {256, 512, 1024, 2048}, menu_last_cx[4] = {128, 256, 512, 1024}, menu_col[7] = {16, 32, 64, 128, 256, 512, 1024};
             pl->tl[a].F = 0;
-            // problems of fewer than 2 M padded samples are at most one wave of row warps: the shortest tile within 10 % of the
-            // fewest samples (measured: c2 31.0 -> 27.3 us, c3 36.9 -> 33.3, c3 Complex 32.0 -> 30.7; 25 %: c2 26.6, c3 35.8 / 34.7).
+            // problems of fewer than 1.28 M padded samples are well under one wave of row warps: the shortest tile within 10 % of the
+            // fewest samples (measured: c2 31.0 -> 27.3 us, c3 36.9 -> 33.3, c3 Complex 32.0 -> 30.7; 25 %: c2 26.6, c3 35.8 / 34.7;
+            // forced on larger problems it loses: 64x200x200 64 -> 77 us, 3000^2 96 -> 108, 8192^2 478 -> 576; tools/run_midsize.py).
             // NDCONV_TILE_SLACK=<percent> (negative: off) and NDCONV_TILE_SMALL_K=<thousand samples> override for experiments
             static const double slack_env = getenv("NDCONV_TILE_SLACK") ? atof(getenv("NDCONV_TILE_SLACK")) / 100.0 : 0.10;
-            static const double small_k = getenv("NDCONV_TILE_SMALL_K") ? atof(getenv("NDCONV_TILE_SMALL_K")) : 2048.0;
+            static const double small_k = getenv("NDCONV_TILE_SMALL_K") ? atof(getenv("NDCONV_TILE_SMALL_K")) : 1280.0;
             double tot = 1; for (int b = 0; b < N; b++) tot *= (double)g.P[b];
             const double slack = tot < small_k * 1000.0 ? slack_env : -1.0;
             if (a == N - 1) fast_pick_tile(g.P[a], g.Kd[a], is_cx ? menu_last_cx : menu_last, 4, &pl->tl[a], slack);
