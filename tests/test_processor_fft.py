@@ -62,6 +62,44 @@ def test_spectrum_of_other_origin_len(ndc):
     proc.close()
 
 
+def test_random_shapes_sweep(ndc):
+    """seeded random ranks 1-4, lengths mixing small, prime, smooth and longer-than-one-tile axes, all four element types:
+    forward against numpy.fft (rotated layout) and forward o backward = id"""
+    pkg, lib = ndc
+    rng = np.random.default_rng(11)
+    proc = pkg.get_fft_processor(0, lib)
+    done = 0
+    while done < 120:
+        nd = int(rng.integers(1, 5))
+        lens = []
+        for _ in range(nd):
+            c = int(rng.integers(0, 4))
+            if c == 0:
+                lens.append(int(rng.integers(1, 40)))
+            elif c == 1:
+                lens.append(int(rng.choice([11, 13, 17, 19, 23, 29, 31, 37, 41, 53, 64, 81, 100, 121, 127])))
+            elif c == 2:
+                lens.append(int(rng.integers(1, 12)))
+            else:
+                lens.append(int(rng.choice([1, 2, 3, 1030, 1100, 2058][: 3 if nd > 2 else 6])))
+        if np.prod(lens) > 400000:
+            continue
+        done += 1
+        dt = [np.float32, np.float64, np.complex64, np.complex128][int(rng.integers(0, 4))]
+        x = rng.standard_normal(lens).astype(dt)
+        if np.iscomplexobj(x):
+            x = x + 1j * rng.standard_normal(lens).astype(dt)
+        spec = proc.forward(x)
+        ref = expected_spectrum(x)
+        eps = np.finfo(np.float32 if dt in (np.float32, np.complex64) else np.float64).eps
+        tol = 8 * eps * np.log2(max(x.size, 2))
+        assert spec.shape == ref.shape, lens
+        assert np.max(np.abs(spec - ref)) <= tol * max(np.max(np.abs(ref)), 1e-30), (lens, dt)
+        back = proc.backward(spec)
+        assert np.max(np.abs(back - x)) <= tol * max(np.max(np.abs(x)), 1e-30), (lens, dt)
+    proc.close()
+
+
 @pytest.mark.gpu
 def test_reference_roundtrip_200x5000(pkg, cuda_lib):
     """real.rs:405-447: 200 x 5000 f32 round trip, tolerance 1e-6"""
