@@ -165,6 +165,13 @@ int ndconv_conv_fft_par(ndconv_processor *p, const ndconv_problem *problem, void
  * with no data-path collective; all handles write into the one `out` array.  Problems too small to pipeline run on
  * processors[0] alone.  Results are those of ndconv_conv_fft up to rounding (slabs may pick other tile lengths). */
 int ndconv_conv_fft_sharded(ndconv_processor *const *processors, int n_processors, const ndconv_problem *problem, void *out);
+/* A batch of INDEPENDENT conv_fft problems distributed whole over processor handles (the reference has no batch call: a user loops
+ * over conv_fft_with_processor, src/conv_fft/mod.rs:404-412): problem i runs on processors[i % n_processors], every
+ * handle from its own host thread on its own stream.  Several handles on one device overlap launches that are each smaller than a
+ * wave; handles on several devices spread the batch over the GPUs.  outs[i] is problem i's output buffer.  Device-resident
+ * problems are only enqueued (synchronise each processor afterwards); host problems are complete on return.  Returns the first
+ * failing status, the remaining problems still run. */
+int ndconv_conv_fft_batch(ndconv_processor *const *processors, int n_processors, const ndconv_problem *problems, void *const *outs, int n_problems);
 
 /* ---- Processor::{forward, backward}, src/conv_fft/processor/mod.rs:91-118 (real.rs:24-281, complex.rs:33-145) --------------
  * N-d FFT with the reference's spectrum layout: `shape` is always the shape of the REAL-SPACE array

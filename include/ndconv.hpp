@@ -263,4 +263,28 @@ Array<T, N> conv_fft_par(const Array<T, N> &x, const K &kernel, const ConvMode<N
     return run<T, N>(pr, NDCONV_PATH_FFT, [&](void *o) { return ndconv_conv_fft_sharded(raw.data(), (int)raw.size(), &pr, o); });
 }
 
+// a batch of independent convolutions with one kernel, distributed whole over the processors (ndconv_conv_fft_batch)
+template <class T, size_t N, class K>
+std::vector<Array<T, N>> conv_fft_batch(const std::vector<Array<T, N>> &xs, const K &kernel, const ConvMode<N> &mode, const PaddingMode<N, T> &pm,
+                                        const std::vector<FftProcessor *> &procs)
+{
+    const auto kwd = into_kernel_with_dilation(kernel);
+    std::vector<ndconv_problem> prs;
+    std::vector<Array<T, N>> outs;
+    std::vector<void *> optr;
+    for (const auto &x : xs) {
+        prs.push_back(lower(x.view(), kwd, mode, pm));
+        int64_t shp[NDCONV_MAX_DIM];
+        check(ndconv_out_shape(&prs.back(), NDCONV_PATH_FFT, shp));
+        std::array<size_t, N> sh;
+        for (size_t i = 0; i < N; i++) sh[i] = (size_t)shp[i];
+        outs.emplace_back(sh);
+    }
+    for (auto &o : outs) optr.push_back(o.data.data());
+    std::vector<ndconv_processor *> raw;
+    for (FftProcessor *p : procs) raw.push_back(p->raw());
+    check(ndconv_conv_fft_batch(raw.data(), (int)raw.size(), prs.data(), optr.data(), (int)prs.size()));
+    return outs;
+}
+
 }  // namespace ndconv

@@ -83,7 +83,7 @@ EXPORTED_SYMBOLS = [
     "ndconv_border_index_map", "ndconv_processor_create", "ndconv_processor_destroy", "ndconv_processor_set_stream",
     "ndconv_processor_synchronize", "ndconv_processor_launch_count", "ndconv_processor_workspace_bytes",
     "ndconv_processor_set_profiling", "ndconv_processor_get_profile",
-    "ndconv_conv_direct", "ndconv_conv_fft", "ndconv_conv_fft_par", "ndconv_conv_fft_sharded", "ndconv_fft_forward", "ndconv_fft_backward",
+    "ndconv_conv_direct", "ndconv_conv_fft", "ndconv_conv_fft_par", "ndconv_conv_fft_sharded", "ndconv_conv_fft_batch", "ndconv_fft_forward", "ndconv_fft_backward",
     "ndconv_slab_plan", "ndconv_host_alloc", "ndconv_host_free",
 ]
 
@@ -121,6 +121,7 @@ class Library:
         for name in ("ndconv_conv_direct", "ndconv_conv_fft", "ndconv_conv_fft_par"):
             getattr(c, name).argtypes = [ctypes.c_void_p, ctypes.POINTER(_Problem), ctypes.c_void_p]
         c.ndconv_conv_fft_sharded.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, ctypes.POINTER(_Problem), ctypes.c_void_p]
+        c.ndconv_conv_fft_batch.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, ctypes.POINTER(_Problem), ctypes.POINTER(ctypes.c_void_p), ctypes.c_int]
         for name in ("ndconv_fft_forward", "ndconv_fft_backward"):
             getattr(c, name).argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
         c.ndconv_slab_plan.argtypes = [ctypes.POINTER(_Problem), ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(_Slab)]
@@ -444,9 +445,12 @@ def conv_fft_with_processor(x, kernel, conv_mode, padding_mode, processor: Proce
     return _run_host("ndconv_conv_fft", PATH_FFT, x, kernel, conv_mode, padding_mode, processor, None)
 
 
-def conv_fft_par(x, kernel, conv_mode=ConvMode.Same, padding_mode=PaddingMode.Zeros, lib=None):
-    """ConvFFTExt::conv_fft_par (src/conv_fft/mod.rs:414-423): same GPU call -- the parallelism is the device's."""
-    return _run_host("ndconv_conv_fft_par", PATH_FFT, x, kernel, conv_mode, padding_mode, None, lib)
+def conv_fft_par(x, kernel, conv_mode=ConvMode.Same, padding_mode=PaddingMode.Zeros, lib=None, processors=None):
+    """ConvFFTExt::conv_fft_par (src/conv_fft/mod.rs:414-423): same GPU call -- the parallelism is the device's; with several
+    `processors` configured (one per GPU) the one convolution is sharded over them (conv_fft_sharded)."""
+    if processors is not None and len(processors) > 1:
+        return conv_fft_sharded(x, kernel, conv_mode, padding_mode, processors)
+    return _run_host("ndconv_conv_fft_par", PATH_FFT, x, kernel, conv_mode, padding_mode, processors[0] if processors else None, lib)
 
 
 def conv_fft_sharded(x, kernel, conv_mode, padding_mode, processors, out=None):
@@ -464,6 +468,25 @@ def conv_fft_sharded(x, kernel, conv_mode, padding_mode, processors, out=None):
     lib.check(lib.c.ndconv_conv_fft_sharded(handles, len(processors), ctypes.byref(pr), out.ctypes.data))
     del keep
     return out
+
+
+def conv_fft_batch(xs, kernels, conv_mode, padding_mode, processors):
+    """independent conv_fft problems distributed whole over processor handles (ndconv_conv_fft_batch): xs[i] * kernels[i] (one
+    kernel for all when `kernels` is not a list) runs on processors[i % len(processors)], each handle on its own host thread."""
+    lib = processors[0].lib
+    xs = [np.asarray(x) for x in xs]
+    ks = kernels if isinstance(kernels, (list, tuple)) else [kernels] * len(xs)
+    prs, keeps, outs = (_Problem * len(xs))(), [], []
+    for i, (x, k) in enumerate(zip(xs, ks)):
+        pr, keep = make_problem(x.shape, [s // x.itemsize for s in x.strides], x.ctypes.data, x.dtype, _into_kwd(k), conv_mode, padding_mode, MEM_HOST, lib)
+        prs[i] = pr
+        keeps.append(keep)
+        outs.append(np.empty(out_shape(pr, PATH_FFT, lib), x.dtype))
+    handles = (ctypes.c_void_p * len(processors))(*[p.handle for p in processors])
+    optr = (ctypes.c_void_p * len(xs))(*[o.ctypes.data for o in outs])
+    lib.check(lib.c.ndconv_conv_fft_batch(handles, len(processors), prs, optr, len(xs)))
+    del keeps
+    return outs
 
 
 def conv_device(entry, processor: Processor, x_ptr, x_shape, x_strides_elems, dtype, kernel, conv_mode, padding_mode, out_ptr, explicit=None):

@@ -1840,6 +1840,34 @@ int ndconv_conv_fft_sharded(ndconv_processor *const *handles, int n_handles, con
     return conv_fft_impl(handles[0], problem, out);
 }
 
+// Independent convolutions distributed whole (north star: "batched independent convolutions are distributed whole"):
+// problem i runs on handle i % n_processors, every handle driven by its own host thread on its own stream and workspace.  Handles on
+// one device overlap their (latency-bound, less-than-a-wave) launches; handles on several devices spread the batch over the GPUs.
+// The first failing status is returned (problems are independent: the others still run).
+int ndconv_conv_fft_batch(ndconv_processor *const *handles, int n_handles, const ndconv_problem *problems, void *const *outs, int n_problems)
+{
+    if (!handles || n_handles < 1 || n_problems < 0 || (n_problems > 0 && (!problems || !outs))) { set_error("conv_fft_batch: bad arguments"); return NDCONV_ERR_BAD_ARG; }
+    for (int i = 0; i < n_handles; i++) if (!handles[i]) { set_error("conv_fft_batch: null processor"); return NDCONV_ERR_BAD_ARG; }
+    const int nt = std::min(n_handles, n_problems);
+    std::vector<int> status((size_t)std::max(nt, 1), NDCONV_OK);
+    std::vector<std::string> message((size_t)std::max(nt, 1));
+    auto work = [&](int h) {
+        for (int i = h; i < n_problems; i += n_handles) {
+            const int st = conv_fft_impl(handles[h], &problems[i], outs[i]);
+            if (st && !status[(size_t)h]) { status[(size_t)h] = st; message[(size_t)h] = get_error(); }      // the error string is thread-local
+        }
+        // device-resident problems are only enqueued: the caller synchronises the processors (ndconv_processor_synchronize)
+    };
+    if (nt <= 1) { if (nt == 1) work(0); }
+    else {
+        std::vector<std::thread> workers;
+        for (int h = 0; h < nt; h++) workers.emplace_back(work, h);
+        for (auto &w : workers) w.join();
+    }
+    for (int h = 0; h < nt; h++) if (status[(size_t)h]) { set_error(message[(size_t)h]); return status[(size_t)h]; }
+    return NDCONV_OK;
+}
+
 void *ndconv_host_alloc(size_t bytes)
 {
 #ifdef NDCONV_CUDA

@@ -158,6 +158,16 @@ static void device_tests()
         auto multi = conv_fft_par(arr, ker, ConvMode<2>::Same(), PaddingMode<2, float>::Zeros(), std::vector<FftProcessor *>{&proc, &proc2});
         auto serial = conv_fft(arr, ker, ConvMode<2>::Same(), PaddingMode<2, float>::Zeros());
         for (size_t i = 0; i < serial.len(); i++) CHECK(std::fabs(serial.data[i] - multi.data[i]) < 1e-4f);
+        // independent problems distributed whole over the processors: ndconv_conv_fft_batch
+        std::vector<Array<float, 2>> xs;
+        for (int b = 0; b < 5; b++) { Array<float, 2> a({20, 24}); for (size_t i = 0; i < a.len(); i++) a.data[i] = (float)((i * (b + 3)) % 11); xs.push_back(a); }
+        auto ys = conv_fft_batch(xs, ker, ConvMode<2>::Full(), PaddingMode<2, float>::Zeros(), std::vector<FftProcessor *>{&proc, &proc2});
+        CHECK(ys.size() == xs.size());
+        for (size_t b = 0; b < xs.size(); b++) {
+            auto one = conv_fft(xs[b], ker, ConvMode<2>::Full(), PaddingMode<2, float>::Zeros());
+            CHECK(one.shape == ys[b].shape);
+            for (size_t i = 0; i < one.len(); i++) CHECK(std::fabs(one.data[i] - ys[b].data[i]) < 1e-4f);
+        }
     });
     run_test("processor::real::round_trip_2d (forward o backward = id, rotated layout [n1/2+1, n0])", [] {
         Array<double, 2> x({6, 10});

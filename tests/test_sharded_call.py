@@ -112,3 +112,26 @@ def test_sharded_pinned_buffers_and_all_devices(pkg, cuda_lib):
     finally:
         cuda_lib.c.ndconv_host_free(ctypes.c_void_p(pin))
         cuda_lib.c.ndconv_host_free(ctypes.c_void_p(pout))
+
+
+def test_batch_distributed_whole(ndc, oracle):
+    """ndconv_conv_fft_batch: independent problems (different shapes) round-robin over three handles, one host thread each"""
+    pkg, lib = ndc
+    rng = np.random.default_rng(8)
+    shapes = [(40, 50), (33, 70), (64, 64), (20, 90), (51, 37), (40, 50), (8, 200)]
+    xs = [rng.random(s, dtype=np.float32) for s in shapes]
+    ks = [rng.random((3 + i % 3, 5), dtype=np.float32) for i in range(len(xs))]
+    procs = [pkg.get_fft_processor(0, lib) for _ in range(3)]
+    outs = pkg.conv_fft_batch(xs, ks, pkg.ConvMode.Same, pkg.PaddingMode.Replicate, procs)
+    assert all(p.launch_count > 0 for p in procs)
+    for x, k, y in zip(xs, ks, outs):
+        ref = oracle.conv_f64_truth(x, k, "same", "replicate")
+        assert y.shape == ref.shape and np.max(np.abs(y - ref)) <= fft_tol(np.float32, 128 * 256, ref)
+    # one kernel for all, fewer problems than handles; a failing problem reports its status
+    outs = pkg.conv_fft_batch(xs[:2], ks[0], pkg.ConvMode.Full, pkg.PaddingMode.Zeros, procs)
+    assert outs[0].shape == (40 + ks[0].shape[0] - 1, 54)
+    with pytest.raises(pkg.NdConvError) as e:
+        pkg.conv_fft_batch([xs[0], np.ones((2, 2), np.float32)], np.ones((3, 3), np.float32), pkg.ConvMode.Valid, pkg.PaddingMode.Zeros, procs)
+    assert e.value.status == pkg.ERR_MISMATCH_SHAPE
+    for p in procs:
+        p.close()
