@@ -84,7 +84,7 @@ EXPORTED_SYMBOLS = [
     "ndconv_processor_synchronize", "ndconv_processor_launch_count", "ndconv_processor_workspace_bytes",
     "ndconv_processor_set_profiling", "ndconv_processor_get_profile",
     "ndconv_conv_direct", "ndconv_conv_fft", "ndconv_conv_fft_par", "ndconv_conv_fft_sharded", "ndconv_conv_fft_batch", "ndconv_fft_forward", "ndconv_fft_backward",
-    "ndconv_slab_plan", "ndconv_host_alloc", "ndconv_host_free",
+    "ndconv_slab_plan", "ndconv_host_alloc", "ndconv_host_free", "ndconv_host_register", "ndconv_host_unregister",
 ]
 
 
@@ -128,6 +128,8 @@ class Library:
         c.ndconv_host_alloc.restype = ctypes.c_void_p
         c.ndconv_host_alloc.argtypes = [ctypes.c_size_t]
         c.ndconv_host_free.argtypes = [ctypes.c_void_p]
+        c.ndconv_host_register.argtypes = [ctypes.c_void_p, ctypes.c_size_t]
+        c.ndconv_host_unregister.argtypes = [ctypes.c_void_p]
 
     def check(self, status):
         if status != 0:
@@ -468,6 +470,26 @@ def conv_fft_sharded(x, kernel, conv_mode, padding_mode, processors, out=None):
     lib.check(lib.c.ndconv_conv_fft_sharded(handles, len(processors), ctypes.byref(pr), out.ctypes.data))
     del keep
     return out
+
+
+class pinned:
+    """context manager: page-lock numpy arrays the caller already owns for the duration of a block of host-resident calls
+    (ndconv_host_register / ndconv_host_unregister)."""
+
+    def __init__(self, *arrays, lib: Library | None = None):
+        self.lib, self.arrays, self.done = lib or get_library(), arrays, []
+
+    def __enter__(self):
+        for a in self.arrays:
+            self.lib.check(self.lib.c.ndconv_host_register(a.ctypes.data, a.nbytes))
+            self.done.append(a)
+        return self
+
+    def __exit__(self, *exc):
+        for a in self.done:
+            self.lib.c.ndconv_host_unregister(a.ctypes.data)
+        self.done = []
+        return False
 
 
 def conv_fft_batch(xs, kernels, conv_mode, padding_mode, processors):

@@ -1887,4 +1887,25 @@ void ndconv_host_free(void *ptr)
 #endif
 }
 
+// page-lock an allocation the caller already owns (an ndarray's Vec): host calls on it then run at the pinned rate.  Registering
+// costs ~0.1 ms per MB (measured, tools/pageable_probe.py) -- worth it for a buffer used by more than ~2 calls, not per call.
+int ndconv_host_register(void *ptr, size_t bytes)
+{
+    if (!ptr || !bytes) { set_error("host_register: bad arguments"); return NDCONV_ERR_BAD_ARG; }
+#ifdef NDCONV_CUDA
+    const cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterDefault);
+    if (e != cudaSuccess) { cudaGetLastError(); set_error(std::string("cudaHostRegister failed: ") + cudaGetErrorString(e)); return NDCONV_ERR_CUDA; }
+#endif
+    return NDCONV_OK;
+}
+int ndconv_host_unregister(void *ptr)
+{
+    if (!ptr) { set_error("host_unregister: bad arguments"); return NDCONV_ERR_BAD_ARG; }
+#ifdef NDCONV_CUDA
+    const cudaError_t e = cudaHostUnregister(ptr);
+    if (e != cudaSuccess) { cudaGetLastError(); set_error(std::string("cudaHostUnregister failed: ") + cudaGetErrorString(e)); return NDCONV_ERR_CUDA; }
+#endif
+    return NDCONV_OK;
+}
+
 }  // extern "C"

@@ -135,3 +135,17 @@ def test_batch_distributed_whole(ndc, oracle):
     assert e.value.status == pkg.ERR_MISMATCH_SHAPE
     for p in procs:
         p.close()
+
+
+@pytest.mark.gpu
+def test_registered_host_arrays(pkg, cuda_lib):
+    """ndconv_host_register: an ordinary numpy array page-locked in place gives the same result as the pageable call"""
+    rng = np.random.default_rng(9)
+    x, k = rng.random((4000, 7000), dtype=np.float32), rng.random((9, 9), dtype=np.float32)
+    proc = pkg.get_fft_processor(0, cuda_lib)
+    a = pkg.conv_fft_with_processor(x, k, pkg.ConvMode.Same, pkg.PaddingMode.Reflect, proc)
+    with pkg.pinned(x, lib=cuda_lib):
+        b = pkg.conv_fft_with_processor(x, k, pkg.ConvMode.Same, pkg.PaddingMode.Reflect, proc)
+    assert np.array_equal(a, b)
+    assert cuda_lib.c.ndconv_host_register(None, 16) == pkg.ERR_BAD_ARG
+    proc.close()
