@@ -196,9 +196,10 @@ int ndconv_slab_plan(const ndconv_problem *problem, int path, int n_slabs, int s
 /* ---- pinned host memory helpers (so callers can stage inputs for full-rate H2D/D2H) ------ */
 void *ndconv_host_alloc(size_t bytes);
 void ndconv_host_free(void *ptr);
-/* Page-lock / release an allocation the caller already owns (the Vec behind an ndarray).  Host-resident calls copy from and to
- * ordinary pageable memory at ~13 GB/s aggregate and at 70-80 GB/s from page-locked memory (8192^2, k = 63^2: 40.7 vs 7.9 ms per
- * call); registering costs ~0.1 ms per MB, so it pays for buffers that serve more than about two calls. */
+/* Page-lock / release an allocation the caller already owns (the Vec behind an ndarray).  Large host-resident calls on ordinary
+ * pageable memory are staged through pinned bounce buffers by host memcpy threads (30-40 GB/s of host<->device traffic; the
+ * driver's own staging gives ~13) and run at 70-80 GB/s from page-locked memory (16384^2, k = 63^2: 57-75 vs 27 ms per call);
+ * registering costs ~0.1 ms per MB, so it pays for buffers that serve more than about two calls. */
 int ndconv_host_register(void *ptr, size_t bytes);
 int ndconv_host_unregister(void *ptr);
 

@@ -192,7 +192,10 @@ struct ndconv_processor {
 #ifdef NDCONV_CUDA
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
 #endif
-    int64_t pipelined_slabs = 0;
+    int64_t pipelined_slabs = 0, bounced_slabs = 0;
+    // pageable host arrays: pinned bounce buffers (cudaHostAlloc) the slabs are staged through by several host memcpy threads
+    void *bounce_in[2] = {nullptr, nullptr}, *bounce_out[2] = {nullptr, nullptr};
+    size_t bounce_in_cap = 0, bounce_out_cap = 0;
     bool l2_limit_set = false;
     size_t held() const
     {
@@ -1273,6 +1276,52 @@ static bool pipeline_eligible(const ndconv_problem *pr, const Geom &g)
     return bytes >= kPipelineMinBytes && g.O[0] >= 4;
 }
 
+// ---- pageable host arrays ---------------------------------------------------------------------------------------------
+// cudaMemcpyAsync from / to ordinary pageable memory is staged by the driver on the calling thread: 13-14 GB/s of host<->device
+// traffic for one thread, ~20 GB/s for two or more (tools/pageable_probe.py, tools/pageable_sharded_probe.py), against 70-80 GB/s
+// from page-locked memory.  A Vec-backed ndarray is pageable, so the pipelined host path stages such arrays itself: several host
+// threads memcpy the slab rows between the caller's array and pinned bounce buffers, and the DMA runs from / to those at full rate.
+struct CopyTask { char *dst; const char *src; size_t bytes; };
+static void parallel_copy(const std::vector<CopyTask> &tasks, int nthreads)
+{
+    size_t total = 0;
+    for (const auto &t : tasks) total += t.bytes;
+    if (!total) return;
+    nthreads = (int)std::max<size_t>(1, std::min<size_t>((size_t)nthreads, total / (4u << 20) + 1));
+    auto work = [&](int w) {
+        const size_t lo = total / nthreads * w, hi = (w == nthreads - 1) ? total : total / nthreads * (w + 1);
+        size_t pos = 0;
+        for (const auto &t : tasks) {
+            const size_t a = std::max(lo, pos), b = std::min(hi, pos + t.bytes);
+            if (a < b) memcpy(t.dst + (a - pos), t.src + (a - pos), b - a);
+            pos += t.bytes;
+            if (pos >= hi) break;
+        }
+    };
+    if (nthreads == 1) { work(0); return; }
+    std::vector<std::thread> th;
+    for (int w = 1; w < nthreads; w++) th.emplace_back(work, w);
+    work(0);
+    for (auto &x : th) x.join();
+}
+static bool host_ptr_is_pageable(const void *ptr)
+{
+    static const bool disabled = getenv("NDCONV_DISABLE_BOUNCE") != nullptr;
+    if (disabled) return false;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, ptr) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeUnregistered;
+}
+static int reserve_bounce(void **buf, size_t *cap, size_t bytes)
+{
+    if (bytes <= *cap && buf[0] && buf[1]) return NDCONV_OK;
+    for (int b = 0; b < 2; b++) { if (buf[b]) cudaFreeHost(buf[b]); buf[b] = nullptr; }
+    *cap = 0;
+    for (int b = 0; b < 2; b++) CU_CHECK(cudaHostAlloc(&buf[b], bytes, cudaHostAllocDefault));
+    *cap = bytes;
+    return NDCONV_OK;
+}
+
 // [o_lo, o_hi): the output rows of axis 0 this call produces (the whole axis for a single-GPU call, one slab of it per GPU in
 // ndconv_conv_fft_sharded); `out` is always the base of the full output array
 static int conv_fft_host_pipelined(ndconv_processor *p, const ndconv_problem *pr, const Geom &g, const std::vector<int32_t> &map0, void *out,
@@ -1313,6 +1362,21 @@ static int conv_fft_host_pipelined(ndconv_processor *p, const ndconv_problem *pr
         st = p->pipe_in[b].reserve((size_t)max_in_rows * in_row_bytes); if (st) return st;
         st = p->pipe_out[b].reserve((size_t)rows * out_row_bytes); if (st) return st;
     }
+    // pageable caller arrays are staged through pinned bounce buffers by host memcpy threads (see parallel_copy)
+    const bool bounce_x = host_ptr_is_pageable(pr->data), bounce_y = host_ptr_is_pageable(out);
+    // measured (16384^2, k = 63^2, 24-core host): driver-staged 164 ms, 8 threads 74.8 ms, 16 threads 56.8 ms, pinned arrays 26.9 ms
+    static const int copy_threads = getenv("NDCONV_HOST_COPY_THREADS") ? std::max(1, atoi(getenv("NDCONV_HOST_COPY_THREADS")))
+                                                                        : (int)std::min(16u, std::max(4u, std::thread::hardware_concurrency() / 2));
+    if (bounce_x) { st = reserve_bounce(p->bounce_in, &p->bounce_in_cap, (size_t)max_in_rows * in_row_bytes); if (st) return st; }
+    if (bounce_y) { st = reserve_bounce(p->bounce_out, &p->bounce_out_cap, (size_t)rows * out_row_bytes); if (st) return st; }
+    struct OutPending { bool live = false; int64_t ob = 0, oe = 0; } pend[2];       // D2H into bounce_out[b] issued, copy-out to the caller's array still due
+    auto drain_tasks = [&](int b, std::vector<CopyTask> &tasks) -> int {              // slab in bounce_out[b] -> caller's rows (after its D2H has finished)
+        if (!pend[b].live) return NDCONV_OK;
+        CU_CHECK(cudaEventSynchronize(p->ev_d2h[b]));
+        tasks.push_back(CopyTask{(char *)out + (size_t)pend[b].ob * out_row_bytes, (const char *)p->bounce_out[b], (size_t)(pend[b].oe - pend[b].ob) * out_row_bytes});
+        pend[b].live = false;
+        return NDCONV_OK;
+    };
     // one host row holding the front / back constants of axis 0 (for constant border rows)
     const bool has_const = g.bf[0] == NDCONV_BORDER_CONST || g.bb[0] == NDCONV_BORDER_CONST;
     std::vector<unsigned char> crow_f, crow_b;
@@ -1344,13 +1408,33 @@ static int conv_fft_host_pipelined(ndconv_processor *p, const ndconv_problem *pr
             i_start = pb + nrow;
         }
         prev_pb = pb; prev_pe = pe;
+        if (bounce_x || bounce_y) {
+            // host side of this slab: rows of x into bounce_in[b] (free once the H2D of slab s-2 has read it), together with the
+            // copy-out of slab s-2 from bounce_out[b] (its D2H was issued a whole iteration ago), on `copy_threads` threads
+            std::vector<CopyTask> tasks;
+            if (bounce_x) {
+                if (sidx >= 2) CU_CHECK(cudaEventSynchronize(p->ev_h2d[b]));
+                for (int64_t i = i_start; i < pe;) {
+                    const int32_t m = map0[(size_t)i];
+                    if (m < 0) { i++; continue; }
+                    int64_t run = 1;
+                    while (i + run < pe && map0[(size_t)(i + run)] == m + (int32_t)run) run++;
+                    tasks.push_back(CopyTask{(char *)p->bounce_in[b] + (size_t)(i - pb) * in_row_bytes, hx + (size_t)m * in_row_bytes, (size_t)run * in_row_bytes});
+                    i += run;
+                }
+            }
+            if (bounce_y) { st = drain_tasks(b, tasks); if (st) return st; }
+            parallel_copy(tasks, copy_threads);
+            p->bounced_slabs++;
+        }
+        const char *hsrc = bounce_x ? (const char *)p->bounce_in[b] : nullptr;       // bounce layout = slab layout: row i at (i - pb)
         for (int64_t i = i_start; i < pe;) {
             const int32_t m = map0[(size_t)i];
             char *drow = din + (size_t)(i - pb) * in_row_bytes;
             if (m >= 0) {
                 int64_t run = 1;
                 while (i + run < pe && map0[(size_t)(i + run)] == m + (int32_t)run) run++;
-                st = be_h2d(drow, hx + (size_t)m * in_row_bytes, (size_t)run * in_row_bytes, p->h2d_stream); if (st) return st;
+                st = be_h2d(drow, hsrc ? hsrc + (size_t)(i - pb) * in_row_bytes : hx + (size_t)m * in_row_bytes, (size_t)run * in_row_bytes, p->h2d_stream); if (st) return st;
                 i += run;
             } else if (m == NDC_MAP_INIT || (m == NDC_MAP_CONST_FRONT && g.bf[0] != NDCONV_BORDER_CONST) || (m == NDC_MAP_CONST_BACK && g.bb[0] != NDCONV_BORDER_CONST)) {
                 CU_CHECK(cudaMemsetAsync(drow, 0, in_row_bytes, p->h2d_stream));
@@ -1376,13 +1460,19 @@ static int conv_fft_host_pipelined(ndconv_processor *p, const ndconv_problem *pr
         CU_CHECK(cudaEventRecord(p->ev_comp[b], comp));
         // ---- D2H ----
         CU_CHECK(cudaStreamWaitEvent(p->d2h_stream, p->ev_comp[b], 0));
-        st = be_d2h(hout + (size_t)ob * out_row_bytes, p->pipe_out[b].p, (size_t)(oe - ob) * out_row_bytes, p->d2h_stream); if (st) return st;
+        st = be_d2h(bounce_y ? (char *)p->bounce_out[b] : hout + (size_t)ob * out_row_bytes, p->pipe_out[b].p, (size_t)(oe - ob) * out_row_bytes, p->d2h_stream); if (st) return st;
         CU_CHECK(cudaEventRecord(p->ev_d2h[b], p->d2h_stream));
+        if (bounce_y) { pend[b].live = true; pend[b].ob = ob; pend[b].oe = oe; }
         p->pipelined_slabs++;
     }
     st = be_sync(p->h2d_stream); if (st) return st;
     st = be_sync(comp); if (st) return st;
     st = be_sync(p->d2h_stream); if (st) return st;
+    if (bounce_y) {
+        std::vector<CopyTask> tasks;
+        for (int b = 0; b < 2; b++) { st = drain_tasks(b, tasks); if (st) return st; }
+        parallel_copy(tasks, copy_threads);
+    }
     return NDCONV_OK;
 }
 #endif
@@ -1706,6 +1796,7 @@ int ndconv_processor_destroy(ndconv_processor *p)
     if (p->aux_stream) { cudaStreamSynchronize(p->aux_stream); cudaStreamDestroy(p->aux_stream); }
     if (p->ev_fork) cudaEventDestroy(p->ev_fork);
     if (p->ev_join) cudaEventDestroy(p->ev_join);
+    for (int b = 0; b < 2; b++) { if (p->bounce_in[b]) cudaFreeHost(p->bounce_in[b]); if (p->bounce_out[b]) cudaFreeHost(p->bounce_out[b]); }
     if (p->h2d_stream) cudaStreamDestroy(p->h2d_stream);
     if (p->d2h_stream) cudaStreamDestroy(p->d2h_stream);
     for (int b = 0; b < 2; b++) { if (p->ev_h2d[b]) cudaEventDestroy(p->ev_h2d[b]); if (p->ev_comp[b]) cudaEventDestroy(p->ev_comp[b]); if (p->ev_d2h[b]) cudaEventDestroy(p->ev_d2h[b]); }
