@@ -620,7 +620,7 @@ static int launch_direct_tile(ndconv_processor *p, const CUtensorMap &tm, const 
     return launch_raw(p->lc(), tp.use_tma ? "direct_conv_tile_tma" : "direct_conv_tile", alg_bytes,
                       [&] {
                           static const bool no_pdl = getenv("NDCONV_DISABLE_PDL") != nullptr;
-                          cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
+                          cudaLaunchConfig_t cfg = {};
                           cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(tile::kThreads); cfg.dynamicSmemBytes = smem; cfg.stream = stm;
                           cudaLaunchAttribute at[1];
                           at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
@@ -949,7 +949,7 @@ static int get_kernel_spectrum(ndconv_processor *p, const ndconv_problem *pr, co
 template <class P> static void launch_pdl(void (*kernel)(const P), int grid, int block, size_t smem, stream_t stm, const P &prm)
 {
     static const bool no_pdl = getenv("NDCONV_DISABLE_PDL") != nullptr;
-    cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
+    cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = smem; cfg.stream = stm;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
