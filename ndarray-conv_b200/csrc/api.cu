@@ -1317,7 +1317,14 @@ static int reserve_bounce(void **buf, size_t *cap, size_t bytes)
     if (bytes <= *cap && buf[0] && buf[1]) return NDCONV_OK;
     for (int b = 0; b < 2; b++) { if (buf[b]) cudaFreeHost(buf[b]); buf[b] = nullptr; }
     *cap = 0;
-    for (int b = 0; b < 2; b++) CU_CHECK(cudaHostAlloc(&buf[b], bytes, cudaHostAllocDefault));
+    for (int b = 0; b < 2; b++) {
+        if (cudaHostAlloc(&buf[b], bytes, cudaHostAllocDefault) != cudaSuccess) {
+            buf[b] = nullptr;
+            if (buf[0]) { cudaFreeHost(buf[0]); buf[0] = nullptr; }
+            set_error("cudaHostAlloc failed for a bounce buffer");
+            return NDCONV_ERR_CUDA;
+        }
+    }
     *cap = bytes;
     return NDCONV_OK;
 }
@@ -1363,12 +1370,13 @@ static int conv_fft_host_pipelined(ndconv_processor *p, const ndconv_problem *pr
         st = p->pipe_out[b].reserve((size_t)rows * out_row_bytes); if (st) return st;
     }
     // pageable caller arrays are staged through pinned bounce buffers by host memcpy threads (see parallel_copy)
-    const bool bounce_x = host_ptr_is_pageable(pr->data), bounce_y = host_ptr_is_pageable(out);
+    bool bounce_x = host_ptr_is_pageable(pr->data), bounce_y = host_ptr_is_pageable(out);
     // measured (16384^2, k = 63^2, 24-core host): driver-staged 164 ms, 8 threads 74.8 ms, 16 threads 56.8 ms, pinned arrays 26.9 ms
     static const int copy_threads = getenv("NDCONV_HOST_COPY_THREADS") ? std::max(1, atoi(getenv("NDCONV_HOST_COPY_THREADS")))
                                                                         : (int)std::min(16u, std::max(4u, std::thread::hardware_concurrency() / 2));
-    if (bounce_x) { st = reserve_bounce(p->bounce_in, &p->bounce_in_cap, (size_t)max_in_rows * in_row_bytes); if (st) return st; }
-    if (bounce_y) { st = reserve_bounce(p->bounce_out, &p->bounce_out_cap, (size_t)rows * out_row_bytes); if (st) return st; }
+    // no pinned memory to be had (locked-memory limit): fall back to the driver's own staging of pageable copies
+    if (bounce_x && reserve_bounce(p->bounce_in, &p->bounce_in_cap, (size_t)max_in_rows * in_row_bytes)) { cudaGetLastError(); bounce_x = false; }
+    if (bounce_y && reserve_bounce(p->bounce_out, &p->bounce_out_cap, (size_t)rows * out_row_bytes)) { cudaGetLastError(); bounce_y = false; }
     struct OutPending { bool live = false; int64_t ob = 0, oe = 0; } pend[2];       // D2H into bounce_out[b] issued, copy-out to the caller's array still due
     auto drain_tasks = [&](int b, std::vector<CopyTask> &tasks) -> int {              // slab in bounce_out[b] -> caller's rows (after its D2H has finished)
         if (!pend[b].live) return NDCONV_OK;
