@@ -149,3 +149,16 @@ def test_registered_host_arrays(pkg, cuda_lib):
     assert np.array_equal(a, b)
     assert cuda_lib.c.ndconv_host_register(None, 16) == pkg.ERR_BAD_ARG
     proc.close()
+
+
+def test_pinned_context_manager_under_emulation(pkg, emul_lib):
+    """pkg.pinned(): register / unregister around host calls (a no-op under host emulation; the device build's cudaHostRegister is
+    covered by test_registered_host_arrays)"""
+    lib = emul_lib
+    assert lib.c.ndconv_host_register(None, 16) == pkg.ERR_BAD_ARG
+    assert lib.c.ndconv_host_unregister(None) == pkg.ERR_BAD_ARG
+    x, k = np.arange(48, dtype=np.float32).reshape(6, 8), np.ones((3, 3), np.float32)
+    a = pkg.conv_fft(x, k, pkg.ConvMode.Same, pkg.PaddingMode.Zeros, lib=lib)
+    with pkg.pinned(x, lib=lib):
+        b = pkg.conv_fft(x, k, pkg.ConvMode.Same, pkg.PaddingMode.Zeros, lib=lib)
+    assert np.array_equal(a, b)
