@@ -9,7 +9,7 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 OUT = PKG / "libndconv_cuda.so"
 SOURCES = [CSRC / "api.cu", CSRC / "host_logic.cpp"]
-HEADERS = sorted(CSRC.glob("*.h")) + sorted(CSRC.glob("*.cuh")) + [PKG.parent / "include" / "ndconv.h"]
+HEADERS = sorted(CSRC.glob("*.h")) + sorted(CSRC.glob("*.cuh")) + sorted(CSRC.glob("*.inc")) + [PKG.parent / "include" / "ndconv.h"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--fmad=true",
               "-Xcompiler", "-fPIC,-O2,-Wall", "-shared", "--expt-relaxed-constexpr"]
 
