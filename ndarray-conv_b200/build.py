@@ -11,7 +11,7 @@ OUT = PKG / "libndconv_cuda.so"
 SOURCES = [CSRC / "api.cu", CSRC / "host_logic.cpp"]
 HEADERS = sorted(CSRC.glob("*.h")) + sorted(CSRC.glob("*.cuh")) + sorted(CSRC.glob("*.inc")) + [PKG.parent / "include" / "ndconv.h"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--fmad=true",
-              "-Xcompiler", "-fPIC,-O2,-Wall", "-shared", "--expt-relaxed-constexpr"]
+              "-Xcompiler", "-fPIC,-O2,-Wall,-Wno-unknown-pragmas", "-shared", "--expt-relaxed-constexpr"]
 
 
 def build_cuda(force: bool = False, verbose: bool = False) -> Path:
