@@ -185,6 +185,22 @@ int ndconv_conv_fft_batch(ndconv_processor *const *processors, int n_processors,
 int ndconv_fft_forward(ndconv_processor *p, int dtype, int ndim, const int64_t *shape, const void *in, void *out, int memory);
 int ndconv_fft_backward(ndconv_processor *p, int dtype, int ndim, const int64_t *shape, const void *spectrum, void *out, int memory);
 
+/* ---- plan introspection (host logic only: works without a device) ---------------------------------------------------------------
+ * What ndconv_conv_fft would do with `problem`: the overlap-save tiling per axis (the analogue of the reference's FFT sizes,
+ * src/conv_fft/good_size.rs:6-42 -- any F >= P is valid and unobservable), the kernel family, the spectra workspace it
+ * needs on the device and whether the call is cut along axis 0. */
+typedef struct ndconv_plan_info {
+    int path;                 /* 0 generic FFT kernels, 1 sm_100a fast path, 2 direct kernel (kernel longer than one FFT tile) */
+    int ndim;
+    int tile_len[6];          /* F_a: transform length of one overlap-save tile */
+    int tile_valid[6];        /* V_a = F_a - Kd_a + 1 alias-free positions per tile */
+    int n_tiles[6];
+    int64_t workspace_bytes;  /* spectra workspace of the whole (unsplit) plan */
+    int64_t split_out_rows;   /* > 0: axis 0 is processed as two sub-convolutions, the first producing this many output rows */
+    int pipelined;            /* host-resident and large: H2D | kernels | D2H overlapped over axis-0 slabs */
+} ndconv_plan_info;
+int ndconv_plan_query(const ndconv_problem *problem, ndconv_plan_info *out);
+
 /* ---- multi-GPU slab planning (overlap-save along axis 0) ---------------------- */
 typedef struct ndconv_slab {
     int64_t out_begin, out_end;   /* output rows [begin,end) of axis 0 owned by this slab */

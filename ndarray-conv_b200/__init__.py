@@ -72,6 +72,11 @@ class _Problem(ctypes.Structure):
     ]
 
 
+class _PlanInfo(ctypes.Structure):
+    _fields_ = [("path", ctypes.c_int), ("ndim", ctypes.c_int), ("tile_len", ctypes.c_int * 6), ("tile_valid", ctypes.c_int * 6),
+                ("n_tiles", ctypes.c_int * 6), ("workspace_bytes", ctypes.c_int64), ("split_out_rows", ctypes.c_int64), ("pipelined", ctypes.c_int)]
+
+
 class _Slab(ctypes.Structure):
     _fields_ = [("out_begin", ctypes.c_int64), ("out_end", ctypes.c_int64), ("pad_begin", ctypes.c_int64), ("pad_end", ctypes.c_int64)]
 
@@ -84,7 +89,7 @@ EXPORTED_SYMBOLS = [
     "ndconv_processor_synchronize", "ndconv_processor_launch_count", "ndconv_processor_workspace_bytes",
     "ndconv_processor_set_profiling", "ndconv_processor_get_profile",
     "ndconv_conv_direct", "ndconv_conv_fft", "ndconv_conv_fft_par", "ndconv_conv_fft_sharded", "ndconv_conv_fft_batch", "ndconv_fft_forward", "ndconv_fft_backward",
-    "ndconv_slab_plan", "ndconv_host_alloc", "ndconv_host_free", "ndconv_host_register", "ndconv_host_unregister",
+    "ndconv_plan_query", "ndconv_slab_plan", "ndconv_host_alloc", "ndconv_host_free", "ndconv_host_register", "ndconv_host_unregister",
 ]
 
 
@@ -124,6 +129,7 @@ class Library:
         c.ndconv_conv_fft_batch.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, ctypes.POINTER(_Problem), ctypes.POINTER(ctypes.c_void_p), ctypes.c_int]
         for name in ("ndconv_fft_forward", "ndconv_fft_backward"):
             getattr(c, name).argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+        c.ndconv_plan_query.argtypes = [ctypes.POINTER(_Problem), ctypes.POINTER(_PlanInfo)]
         c.ndconv_slab_plan.argtypes = [ctypes.POINTER(_Problem), ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(_Slab)]
         c.ndconv_host_alloc.restype = ctypes.c_void_p
         c.ndconv_host_alloc.argtypes = [ctypes.c_size_t]
@@ -544,6 +550,21 @@ class PreparedConv:
         st = self.fn(self.processor.handle, self._ref, ctypes.c_void_p(out_ptr))
         if st:
             self.lib.check(st)
+
+
+def plan_query(x_shape, dtype, kernel, conv_mode, padding_mode, memory=MEM_DEVICE, lib=None):
+    """what conv_fft would do with this problem (ndconv_plan_query; host logic only): dict(path, tile_len, tile_valid, n_tiles,
+    workspace_bytes, split_out_rows, pipelined)"""
+    lib = lib or get_library()
+    kwd = _into_kwd(kernel)
+    strides = [int(np.prod(x_shape[i + 1:])) for i in range(len(x_shape))]
+    pr, keep = make_problem(tuple(x_shape), strides, 1, dtype, kwd, conv_mode, padding_mode, memory, lib)     # data pointer unused by the planner
+    info = _PlanInfo()
+    lib.check(lib.c.ndconv_plan_query(ctypes.byref(pr), ctypes.byref(info)))
+    nd = info.ndim
+    return {"path": ("generic", "fast", "direct")[info.path], "tile_len": list(info.tile_len[:nd]), "tile_valid": list(info.tile_valid[:nd]),
+            "n_tiles": list(info.n_tiles[:nd]), "workspace_bytes": int(info.workspace_bytes), "split_out_rows": int(info.split_out_rows),
+            "pipelined": bool(info.pipelined)}
 
 
 def slab_plan(x_shape, dtype, kernel, conv_mode, padding_mode, path, n_slabs, slab, lib=None):

@@ -701,6 +701,40 @@ int ndconv_fft_backward(ndconv_processor *p, int dtype, int ndim, const int64_t 
     return fft_nd(p, dtype, ndim, shape, spectrum, out, memory, true);
 }
 
+// what conv_fft would do with this problem: host logic only (no device needed), for memory planning and for pinning the planner
+int ndconv_plan_query(const ndconv_problem *problem, ndconv_plan_info *out)
+{
+    if (!out) { set_error("plan_query: null output"); return NDCONV_ERR_BAD_ARG; }
+    memset(out, 0, sizeof(*out));
+    Geom g; std::vector<int32_t> maps[NDC_MAX_DIM];
+    int st = check_problem(problem, NDCONV_PATH_FFT, &g, maps); if (st) return st;
+    out->ndim = g.ndim;
+    if (kernel_exceeds_fft_tiles(problem)) { out->path = 2; return NDCONV_OK; }       // evaluated by the direct kernel
+    PlanEntry e;
+    st = make_plan(g, &e.pl); if (st) return st;
+    plan_axis0_split(problem, g, e.pl, &e);
+    const FftPlan &pl = e.pl;
+    out->path = pl.fast ? 1 : 0;
+    for (int a = 0; a < g.ndim; a++) { out->tile_len[a] = pl.tl[a].F; out->tile_valid[a] = pl.tl[a].V; out->n_tiles[a] = pl.tl[a].ntiles; }
+    const int al = g.ndim - 1;
+    int64_t elems = pl.ntiles_total;
+    if (pl.fast) {
+        const int L = pl.is_cx ? pl.tl[al].F : pl.tl[al].F / 2;
+        elems *= (int64_t)(pl.is_cx ? L : L + 8);                                       // row pitch of the fast path's workspace (kPad = 8)
+        for (int a = 0; a < al; a++) elems *= pl.tl[a].F;
+        if (g.ndim == 1) elems = 0;                                                     // rank 1 is one fused launch: no workspace
+    } else {
+        elems *= pl.tile_elems;
+        if (g.ndim == 1) elems = 0;
+    }
+    const size_t csz = (g.dtype == NDCONV_F64 || g.dtype == NDCONV_C64) ? 16 : 8;
+    out->workspace_bytes = elems * (int64_t)csz;
+    out->split_out_rows = e.split_out;
+    out->pipelined = (problem->memory == NDCONV_MEM_HOST && g.data_contiguous &&
+                      ((size_t)g.data_total + (size_t)g.out_total) * g.es >= ((size_t)96 << 20) && g.O[0] >= 4) ? 1 : 0;
+    return NDCONV_OK;
+}
+
 int ndconv_slab_plan(const ndconv_problem *problem, int path, int n_slabs, int slab, ndconv_slab *out)
 {
     Geom g; std::vector<int32_t> maps[NDC_MAX_DIM];
