@@ -821,25 +821,29 @@ struct ColParams {
     int skip;               // modes 1 / 2: the first `skip` rows of the axis (= Kd - 1, the aliased head the crop discards) are not stored
 };
 
-template <int E, int Tc> struct ColCfg {
+// EARLY (experiment, NDCONV_COL_EARLY=1, not yet measured): a half-item staging buffer of its own (rows [0, F/2) of the next item)
+// that is free as soon as the registers are loaded, so half of the next item is prefetched at the START of an item instead of
+// just before the last butterfly; rows [F/2, F) are staged late into the exchange buffer as in the default kernel.
+template <int E, int Tc, bool EARLY = false> struct ColCfg {
     static constexpr int F = E * Tc, Mc = E / Tc;
     static constexpr int threads = Tc * 8;
     static constexpr int pitch = Tc * 8 + 8;                             // padded k1-row stride of the exchange buffer
     static constexpr int ex = (E * pitch > F * 8 ? E * pitch : F * 8);
-    static constexpr int smem = ((Tc == E ? 1 : 2) * F + ex) * 8;         // forward table, transposed table for the inverse when Tc != E, exchange buffer
+    static constexpr int smem = ((Tc == E ? 1 : 2) * F + ex + (EARLY ? F * 4 : 0)) * 8;   // forward table, transposed table for the inverse when Tc != E, exchange buffer, half-item buffer
     static constexpr int min_blocks = (E == 32 && Tc == 32) ? 2 : 4;      // 512-row tiles: 4 CTAs of 128 threads at 126 registers beat 3 at 168 (s512: 52 -> 48 us)
 };
 
-template <int E, int Tc>
-__global__ void __launch_bounds__(ColCfg<E, Tc>::threads, ColCfg<E, Tc>::min_blocks) col_pass(const __grid_constant__ ColParams p)
+template <int E, int Tc, bool EARLY = false>
+__global__ void __launch_bounds__(ColCfg<E, Tc, EARLY>::threads, ColCfg<E, Tc, EARLY>::min_blocks) col_pass(const __grid_constant__ ColParams p)
 {
     pdl_launch_dependents();
-    using C = ColCfg<E, Tc>;
+    using C = ColCfg<E, Tc, EARLY>;
     constexpr int F = C::F, Mc = C::Mc, pitch = C::pitch;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     pc *s_tw = reinterpret_cast<pc *>(smem_raw);        // s_tw[k1 * Tc + i] = W_F^{i k1}, k1 < E, i < Tc   (forward: i is the thread index)
     pc *s_twT = s_tw + F;                               // s_twT[ii * E + k1] = W_F^{ii k1}   (inverse, Tc != E: k1 is the thread-dependent index)
     pc *S = s_tw + (Tc == E ? 1 : 2) * F;
+    [[maybe_unused]] pc *S2 = S + C::ex;                // EARLY: rows [0, F/2) of the staged item, S2[row * 8 + column]
     const int tid = threadIdx.x;
     const int c = tid & 7, i = tid >> 3;                // column of the block, thread index inside the column (< Tc)
     for (int idx = tid; idx < F; idx += C::threads) { s_tw[idx] = ld_pc(p.tw + (idx / Tc) * (idx % Tc)); if (Tc != E) s_twT[idx] = ld_pc(p.tw + (idx / E) * (idx % E)); }
@@ -863,9 +867,23 @@ __global__ void __launch_bounds__(ColCfg<E, Tc>::threads, ColCfg<E, Tc>::min_blo
         }
         cp_async_commit();
     };
+    // EARLY: the two halves of an item, staged separately (rows < F/2 -> S2, rows >= F/2 -> their usual place in S)
+    constexpr int kHalfChunks = (F * 2 + C::threads - 1) / C::threads;
+    [[maybe_unused]] auto prefetch_half = [&](const Item &it, bool hi) {
+        const cf *gn = p.ws + it.off;
+#pragma unroll
+        for (int m = 0; m < kHalfChunks; m++) {
+            const int id = tid + C::threads * m, row = (id >> 2) + (hi ? F / 2 : 0), part = id & 3;
+            if (F * 2 % C::threads == 0 || id < F * 2) cp_async16((hi ? S : S2) + row * 8 + part * 2, gn + (int64_t)row * p.inner + part * 2);
+        }
+        cp_async_commit();
+    };
     pdl_wait();                                      // before the first access to the workspace (the table staging above reads constants)
     Item nxt; nxt.off = 0; nxt.rel = 0;
-    if ((int64_t)blockIdx.x < p.nwork) { nxt = decode(blockIdx.x); prefetch(nxt); }
+    if ((int64_t)blockIdx.x < p.nwork) {
+        nxt = decode(blockIdx.x);
+        if constexpr (EARLY) { prefetch_half(nxt, false); prefetch_half(nxt, true); } else prefetch(nxt);
+    }
     for (int64_t w = blockIdx.x; w < p.nwork; w += gridDim.x) {
         const Item cur = nxt;
         cf *gt = p.ws + cur.off + c;
@@ -875,8 +893,9 @@ __global__ void __launch_bounds__(ColCfg<E, Tc>::threads, ColCfg<E, Tc>::min_blo
         if (p.mode != 1) {
             // ---- forward: rows i + Tc j -> radix E -> twiddle -> exchange -> radix Tc -> rows q = (i + Tc m) + E k2 ----
 #pragma unroll
-            for (int j = 0; j < E; j++) v[j] = S[(i + Tc * j) * 8 + c];
+            for (int j = 0; j < E; j++) v[j] = ((EARLY && j < E / 2) ? S2 : S)[(i + Tc * j) * 8 + c];      // row i + Tc j < F/2 <=> j < E/2
             __syncthreads();
+            if constexpr (EARLY) { if (w + gridDim.x < p.nwork) { nxt = decode(w + gridDim.x); prefetch_half(nxt, false); } }   // S2 is free: first half of the next item
             pk::dft<false, E>(v);
 #pragma unroll
             for (int k1 = 0; k1 < E; k1++) S[k1 * pitch + i * 8 + c] = pk::cmul(v[k1], s_tw[k1 * Tc + i]);
@@ -898,11 +917,11 @@ __global__ void __launch_bounds__(ColCfg<E, Tc>::threads, ColCfg<E, Tc>::min_blo
 #pragma unroll
             for (int m = 0; m < Mc; m++)
 #pragma unroll
-                for (int k2 = 0; k2 < Tc; k2++) v[m * Tc + k2] = S[(i + Tc * m + E * k2) * 8 + c];
+                for (int k2 = 0; k2 < Tc; k2++) v[m * Tc + k2] = ((EARLY && k2 < Tc / 2) ? S2 : S)[(i + Tc * m + E * k2) * 8 + c];   // row < F/2 <=> k2 < Tc/2
         }
         if (p.mode == 0) {
             __syncthreads();                               // all exchange reads done: S may be restaged
-            if (w + gridDim.x < p.nwork) { nxt = decode(w + gridDim.x); prefetch(nxt); }
+            if (w + gridDim.x < p.nwork) { if constexpr (EARLY) prefetch_half(nxt, true); else { nxt = decode(w + gridDim.x); prefetch(nxt); } }
 #pragma unroll
             for (int m = 0; m < Mc; m++)
 #pragma unroll
@@ -914,6 +933,7 @@ __global__ void __launch_bounds__(ColCfg<E, Tc>::threads, ColCfg<E, Tc>::min_blo
             // so the inverse is the forward flow with conjugated twiddles (no transposed table needed)
             pk::dft<true, E>(v);
             __syncthreads();                               // every thread has finished reading S
+            if constexpr (EARLY) { if (p.mode == 1 && w + gridDim.x < p.nwork) { nxt = decode(w + gridDim.x); prefetch_half(nxt, false); } }
 #pragma unroll
             for (int n1 = 0; n1 < E; n1++) S[n1 * pitch + i * 8 + c] = pk::cmulc(v[n1], s_tw[n1 * Tc + i]);
             __syncthreads();
@@ -925,6 +945,7 @@ __global__ void __launch_bounds__(ColCfg<E, Tc>::threads, ColCfg<E, Tc>::min_blo
 #pragma unroll
             for (int m = 0; m < Mc; m++) pk::dft<true, Tc>(v + m * Tc);
             __syncthreads();                               // every thread has finished reading S
+            if constexpr (EARLY) { if (p.mode == 1 && w + gridDim.x < p.nwork) { nxt = decode(w + gridDim.x); prefetch_half(nxt, false); } }
 #pragma unroll
             for (int m = 0; m < Mc; m++)
 #pragma unroll
@@ -935,7 +956,7 @@ __global__ void __launch_bounds__(ColCfg<E, Tc>::threads, ColCfg<E, Tc>::min_blo
             for (int k1 = 0; k1 < E; k1++) v[k1] = S[k1 * pitch + i * 8 + c];
             __syncthreads();
         }
-        if (w + gridDim.x < p.nwork) { nxt = decode(w + gridDim.x); prefetch(nxt); }
+        if (w + gridDim.x < p.nwork) { if constexpr (EARLY) prefetch_half(nxt, true); else { nxt = decode(w + gridDim.x); prefetch(nxt); } }
         pk::dft<true, E>(v);
 #pragma unroll
         for (int j = 0; j < E; j++) if (i + Tc * j >= p.skip) st_pc(gt + (int64_t)(i + Tc * j) * p.inner, v[j]);
