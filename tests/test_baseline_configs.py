@@ -6,7 +6,11 @@ checked through properties the domain offers, on device-resident data:
   * a one-tap kernel turns the convolution into a pure shift of the Reflect-padded input (checked against torch F.pad),
   * random outputs (corners, edges, interior) against float64 direct evaluation of the 63x63 taps,
   * linearity in the data: conv(a*x + b*z) = a*conv(x) + b*conv(z),
-  * a constant input gives c * sum(k) everywhere under Reflect.
+  * a constant input gives c * sum(k) everywhere under Reflect;
+and, since round 2, three FULL 4096-row bands of the output against the oracle's float64 evaluation of the reference pipeline
+(scipy-pocketfft restatement, oracle.conv_fft_scipy) on exactly the input rows those bands read: the top edge, an interior band
+across tile seams, and the bottom band that holds the axis-0 tile seams 29822 / 30784 / 31746, the axis-0 split row 32708 and
+the bottom Reflect edge.
 """
 import numpy as np
 import pytest
@@ -125,4 +129,43 @@ def test_c5_full_size_properties(pkg, cuda_lib):
     run(xc, kr, full)
     assert float((full[:4096] - lin).abs().max()) <= 3 * tol_rel * float(lin.abs().max())
     del y3
+    proc.close()
+
+
+def test_c5_full_bands_against_oracle(pkg, cuda_lib, oracle):
+    """c5 at full size on the device; bands of 4096 output rows (all 32830 columns) against the float64 oracle.  A band of output
+    rows [r0, r0 + B) reads padded rows [r0, r0 + B + Kd0 - 1) of axis 0; the Reflect border of axis 0 is resolved here by index
+    (rows of the device array are fetched through the reflected index), and the oracle then runs the band as
+    ConvMode::Explicit{axis 0: no padding, axis 1: 62 | 62} with Reflect on axis 1 -- the overlap-save identity of SURVEY 8e."""
+    torch = pytest.importorskip("torch")
+    n, K = 32768, 63
+    dev = torch.device("cuda", 0)
+    proc = pkg.get_fft_processor(0, cuda_lib)
+    g = torch.Generator(device=dev).manual_seed(1005)
+    x = torch.rand((n, n), generator=g, device=dev, dtype=torch.float32)
+    O = n + K - 1
+    y = torch.empty((O, O), device=dev, dtype=torch.float32)
+    kr = np.random.default_rng(2005).random((K, K), dtype=np.float32)
+    torch.cuda.synchronize(dev)
+    pkg.conv_device("ndconv_conv_fft", proc, x.data_ptr(), (n, n), (n, 1), np.float32, kr, pkg.ConvMode.Full, pkg.PaddingMode.Reflect, y.data_ptr())
+    proc.synchronize()
+    info = pkg.plan_query((n, n), np.float32, kr, pkg.ConvMode.Full, pkg.PaddingMode.Reflect, lib=cuda_lib)
+    V0 = info["tile_valid"][0]
+    B = 4096
+    seam = (17 * V0) - B // 2                                  # an interior band with axis-0 tile seams inside it
+    eps = float(np.finfo(np.float32).eps)
+    for r0 in (0, seam, O - B):
+        pr = torch.arange(r0, r0 + B + K - 1, device=dev) - (K - 1)            # source row of each padded row, before reflection
+        pr = torch.where(pr < 0, -pr, pr)
+        pr = torch.where(pr >= n, 2 * (n - 1) - pr, pr)
+        xb = x.index_select(0, pr).cpu().numpy().astype(np.float64)
+        ref = oracle.conv_fft_scipy(xb, kr.astype(np.float64), ("explicit", [[0, 0], [K - 1, K - 1]], [1, 1]),
+                                    ("explicit", [["zeros", "zeros"], ["reflect", "reflect"]]), 1, True, workers=__import__("os").cpu_count() or 1)
+        got = y[r0:r0 + B].cpu().numpy().astype(np.float64)
+        assert ref.shape == got.shape == (B, O)
+        scale = float(np.max(np.abs(ref)))
+        err = float(np.max(np.abs(got - ref)))
+        tol = 4 * eps * np.log2(1024 * 2048) * scale
+        print(f"c5 band rows [{r0}, {r0 + B}): max|err| = {err:.3e}, tol = {tol:.3e}, max|out| = {scale:.1f}")
+        assert err <= tol, (r0, err, tol)
     proc.close()
