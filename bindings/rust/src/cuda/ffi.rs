@@ -92,6 +92,26 @@ pub struct ndconv_plan_info {
 }
 
 #[repr(C)]
+#[derive(Clone, Copy)]
+pub struct ndconv_shard {
+    pub data: *mut c_void,
+    pub rows: i64,
+    pub halo_front: i64,
+    pub halo_back: i64,
+    pub out: *mut c_void,
+}
+
+#[repr(C)]
+#[derive(Clone, Copy, Default)]
+pub struct ndconv_shard_info {
+    pub out_begin: i64,
+    pub out_end: i64,
+    pub halo_front: i64,
+    pub halo_back: i64,
+    pub first_row: i64,
+}
+
+#[repr(C)]
 #[derive(Clone, Copy, Default)]
 pub struct ndconv_slab {
     pub out_begin: i64,
@@ -130,8 +150,9 @@ extern "C" {
     pub fn ndconv_conv_fft(p: *mut ndconv_processor, problem: *const ndconv_problem, out: *mut c_void) -> c_int;
     pub fn ndconv_conv_fft_par(p: *mut ndconv_processor, problem: *const ndconv_problem, out: *mut c_void) -> c_int;
     pub fn ndconv_conv_fft_sharded(processors: *const *mut ndconv_processor, n_processors: c_int, problem: *const ndconv_problem, out: *mut c_void) -> c_int;
+    pub fn ndconv_shard_plan(problem: *const ndconv_problem, n_shards: c_int, shard_rows: *const i64, shard: c_int, out: *mut ndconv_shard_info) -> c_int;
     pub fn ndconv_conv_fft_sharded_device(processors: *const *mut ndconv_processor, n_processors: c_int, problem: *const ndconv_problem,
-                                          shard_data: *const *const c_void, shard_rows: *const i64, shard_out: *const *mut c_void) -> c_int;
+                                          shards: *const ndconv_shard) -> c_int;
     pub fn ndconv_conv_fft_batch(processors: *const *mut ndconv_processor, n_processors: c_int, problems: *const ndconv_problem,
                                  outs: *const *mut c_void, n_problems: c_int) -> c_int;
     // ---- Processor::{forward, backward} ----

@@ -50,7 +50,8 @@ typedef enum ndconv_dtype {
     NDCONV_I32 = 0, NDCONV_I64 = 1, NDCONV_F32 = 2, NDCONV_F64 = 3,
     NDCONV_C32 = 4, /* num::Complex<f32>, interleaved re,im */
     NDCONV_C64 = 5, /* num::Complex<f64> */
-    NDCONV_I8 = 6, NDCONV_I16 = 7, NDCONV_U8 = 8, NDCONV_U16 = 9, NDCONV_U32 = 10, NDCONV_U64 = 11
+    NDCONV_I8 = 6, NDCONV_I16 = 7, NDCONV_U8 = 8, NDCONV_U16 = 9, NDCONV_U32 = 10, NDCONV_U64 = 11,
+    NDCONV_I128 = 12, NDCONV_U128 = 13 /* Rust i128 / u128: 16 bytes, little-endian, direct conv only (wrapping, as in release builds) */
 } ndconv_dtype;
 
 /* BorderType<T>, src/lib.rs:131-143 */
@@ -165,6 +166,31 @@ int ndconv_conv_fft_par(ndconv_processor *p, const ndconv_problem *problem, void
  * with no data-path collective; all handles write into the one `out` array.  Problems too small to pipeline run on
  * processors[0] alone.  Results are those of ndconv_conv_fft up to rounding (slabs may pick other tile lengths). */
 int ndconv_conv_fft_sharded(ndconv_processor *const *processors, int n_processors, const ndconv_problem *problem, void *out);
+/* The same convolution when the array is ALREADY DEVICE-RESIDENT and partitioned along axis 0 (SURVEY 2.2 K10, 8e "Collective"; no
+ * reference analogue): shard g -- processors[g], on its own device -- owns the contiguous rows [r_g, r_g + shards[g].rows) of the
+ * data in standard layout (inner extents as in problem->data_shape; problem->data / data_strides / memory are ignored), with
+ * ghost rows: shards[g].data points at the first OWNED row and the allocation extends halo_front rows before and halo_back rows
+ * after the owned rows.  The call fills the ghost rows each shard needs -- the (Kd0 - 1)-row halos of its neighbours, or the far
+ * end of the array for a Circular border on axis 0 -- with peer-to-peer copies over NVLink (cudaMemcpyPeerAsync on the consumer's
+ * stream; nothing is re-materialised, the owned rows are never copied) and enqueues the single-GPU pipeline on every shard in
+ * place; the true array edges keep their border rule.  Shard g produces output rows [out_begin, out_end) of ndconv_shard_plan
+ * (the balanced split of ndconv_slab_plan) into shards[g].out, contiguous.  Like every device-resident call it returns once the
+ * work is enqueued: the shard data must be complete on entry; synchronise each processor afterwards.  One host thread per shard. */
+typedef struct ndconv_shard {
+    void *data;          /* first owned row, device pointer on processors[g]'s device */
+    int64_t rows;        /* owned rows of axis 0 (the shards tile [0, data_shape[0]) in order) */
+    int64_t halo_front;  /* writable ghost rows available before / after the owned rows */
+    int64_t halo_back;
+    void *out;           /* output rows of this shard */
+} ndconv_shard;
+typedef struct ndconv_shard_info {
+    int64_t out_begin, out_end;        /* output rows of axis 0 this shard produces */
+    int64_t halo_front, halo_back;     /* ghost rows the call will fill (0 at a true array edge unless the border is Circular) */
+    int64_t first_row;                 /* global index of the shard's first owned row */
+} ndconv_shard_info;
+/* host logic only (no device): what shard `shard` of `n_shards` (owned row counts in shard_rows[]) produces and needs */
+int ndconv_shard_plan(const ndconv_problem *problem, int n_shards, const int64_t *shard_rows, int shard, ndconv_shard_info *out);
+int ndconv_conv_fft_sharded_device(ndconv_processor *const *processors, int n_processors, const ndconv_problem *problem, const ndconv_shard *shards);
 /* A batch of INDEPENDENT conv_fft problems distributed whole over processor handles (the reference has no batch call: a user loops
  * over conv_fft_with_processor, src/conv_fft/mod.rs:404-412): problem i runs on processors[i % n_processors], every
  * handle from its own host thread on its own stream.  Several handles on one device overlap launches that are each smaller than a

@@ -34,10 +34,46 @@ ERR_CUDA, ERR_INTERNAL = 100, 101
 PATH_DIRECT, PATH_FFT = 0, 1
 MEM_HOST, MEM_DEVICE = 0, 1
 
+# Rust i128 / u128 have no numpy scalar type: 16-byte little-endian records (lo, hi); int128_array / int128_values convert
+I128 = np.dtype([("lo", "<u8"), ("hi", "<i8")])
+U128 = np.dtype([("lo", "<u8"), ("hi", "<u8")])
+
+
+def int128_array(values, signed=True):
+    """nested sequence (or numpy array) of Python ints -> array of I128 / U128 records (two's complement, wrapping mod 2^128)"""
+    obj = np.asarray(values, dtype=object)
+    out = np.zeros(obj.shape, I128 if signed else U128)
+    flat_lo, flat_hi = out["lo"].reshape(-1), out["hi"].reshape(-1)
+    for i, v in enumerate(obj.reshape(-1)):
+        u = int(v) % (1 << 128)
+        flat_lo[i] = u & ((1 << 64) - 1)
+        h = u >> 64
+        flat_hi[i] = h - (1 << 64) if (signed and h >= (1 << 63)) else h
+    return out
+
+
+def int128_values(arr):
+    """array of I128 / U128 records -> object array of Python ints"""
+    arr = np.asarray(arr)
+    signed = arr.dtype == I128
+    lo, hi = arr["lo"].astype(object), arr["hi"].astype(object)
+    v = (hi % (1 << 64)) * (1 << 64) + lo
+    if signed:
+        v = np.where(v >= (1 << 127), v - (1 << 128), v)
+    return v
+
+
+def _scalar_bytes(value, dtype):
+    if dtype in (I128, U128):
+        return (int(value) % (1 << 128)).to_bytes(16, "little")
+    return np.asarray(value, dtype=dtype).tobytes()
+
+
 DTYPE_CODES = {
     np.dtype(np.int32): 0, np.dtype(np.int64): 1, np.dtype(np.float32): 2, np.dtype(np.float64): 3,
     np.dtype(np.complex64): 4, np.dtype(np.complex128): 5, np.dtype(np.int8): 6, np.dtype(np.int16): 7,
     np.dtype(np.uint8): 8, np.dtype(np.uint16): 9, np.dtype(np.uint32): 10, np.dtype(np.uint64): 11,
+    I128: 12, U128: 13,
 }
 
 
@@ -81,6 +117,15 @@ class _Slab(ctypes.Structure):
     _fields_ = [("out_begin", ctypes.c_int64), ("out_end", ctypes.c_int64), ("pad_begin", ctypes.c_int64), ("pad_end", ctypes.c_int64)]
 
 
+class _Shard(ctypes.Structure):
+    _fields_ = [("data", ctypes.c_void_p), ("rows", ctypes.c_int64), ("halo_front", ctypes.c_int64), ("halo_back", ctypes.c_int64), ("out", ctypes.c_void_p)]
+
+
+class _ShardInfo(ctypes.Structure):
+    _fields_ = [("out_begin", ctypes.c_int64), ("out_end", ctypes.c_int64), ("halo_front", ctypes.c_int64), ("halo_back", ctypes.c_int64),
+                ("first_row", ctypes.c_int64)]
+
+
 # every symbol include/ndconv.h declares (tests check the built library exports all of them)
 EXPORTED_SYMBOLS = [
     "ndconv_version", "ndconv_is_emulation", "ndconv_last_error_string", "ndconv_status_string", "ndconv_dtype_size",
@@ -88,7 +133,7 @@ EXPORTED_SYMBOLS = [
     "ndconv_border_index_map", "ndconv_processor_create", "ndconv_processor_destroy", "ndconv_processor_set_stream",
     "ndconv_processor_synchronize", "ndconv_processor_launch_count", "ndconv_processor_workspace_bytes",
     "ndconv_processor_set_profiling", "ndconv_processor_get_profile",
-    "ndconv_conv_direct", "ndconv_conv_fft", "ndconv_conv_fft_par", "ndconv_conv_fft_sharded", "ndconv_conv_fft_batch", "ndconv_fft_forward", "ndconv_fft_backward",
+    "ndconv_conv_direct", "ndconv_conv_fft", "ndconv_conv_fft_par", "ndconv_conv_fft_sharded", "ndconv_shard_plan", "ndconv_conv_fft_sharded_device", "ndconv_conv_fft_batch", "ndconv_fft_forward", "ndconv_fft_backward",
     "ndconv_plan_query", "ndconv_slab_plan", "ndconv_host_alloc", "ndconv_host_free", "ndconv_host_register", "ndconv_host_unregister",
 ]
 
@@ -130,6 +175,8 @@ class Library:
         for name in ("ndconv_fft_forward", "ndconv_fft_backward"):
             getattr(c, name).argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
         c.ndconv_plan_query.argtypes = [ctypes.POINTER(_Problem), ctypes.POINTER(_PlanInfo)]
+        c.ndconv_shard_plan.argtypes = [ctypes.POINTER(_Problem), ctypes.c_int, ctypes.POINTER(ctypes.c_int64), ctypes.c_int, ctypes.POINTER(_ShardInfo)]
+        c.ndconv_conv_fft_sharded_device.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, ctypes.POINTER(_Problem), ctypes.POINTER(_Shard)]
         c.ndconv_slab_plan.argtypes = [ctypes.POINTER(_Problem), ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(_Slab)]
         c.ndconv_host_alloc.restype = ctypes.c_void_p
         c.ndconv_host_alloc.argtypes = [ctypes.c_size_t]
@@ -346,7 +393,7 @@ def make_problem(x_shape, x_strides_elems, x_ptr, dtype, kernel: KernelWithDilat
             b = borders[i][s]
             pr.border[i][s].type = b.kind
             if b.kind == BorderType.CONST:
-                raw = np.asarray(b.value, dtype=dtype).tobytes()
+                raw = _scalar_bytes(b.value, dtype)
                 for j, byte in enumerate(raw):
                     pr.border[i][s].value[j] = byte
     return pr, (k,)
@@ -476,6 +523,38 @@ def conv_fft_sharded(x, kernel, conv_mode, padding_mode, processors, out=None):
     lib.check(lib.c.ndconv_conv_fft_sharded(handles, len(processors), ctypes.byref(pr), out.ctypes.data))
     del keep
     return out
+
+
+def _global_problem(x_shape, dtype, kernel, conv_mode, padding_mode, lib):
+    strides = [int(np.prod(x_shape[i + 1:])) for i in range(len(x_shape))]
+    dummy = np.zeros(1, dtype)                        # the data pointer of the global problem is never dereferenced, but must not be null
+    pr, keep = make_problem(x_shape, strides, dummy.ctypes.data, dtype, _into_kwd(kernel), conv_mode, padding_mode, MEM_DEVICE, lib)
+    return pr, keep + (dummy,)
+
+
+def shard_plan(x_shape, dtype, kernel, conv_mode, padding_mode, shard_rows, shard, lib=None):
+    """ndconv_shard_plan: output rows shard `shard` produces and the ghost rows ndconv_conv_fft_sharded_device fills around its
+    owned rows, for an array partitioned along axis 0 into len(shard_rows) device-resident shards (host logic only)."""
+    lib = lib or get_library()
+    pr, keep = _global_problem(x_shape, dtype, kernel, conv_mode, padding_mode, lib)
+    rows = (ctypes.c_int64 * len(shard_rows))(*[int(r) for r in shard_rows])
+    info = _ShardInfo()
+    lib.check(lib.c.ndconv_shard_plan(ctypes.byref(pr), len(shard_rows), rows, shard, ctypes.byref(info)))
+    return {k: int(getattr(info, k)) for k, _ in _ShardInfo._fields_}
+
+
+def conv_fft_sharded_device(processors, x_shape, dtype, kernel, conv_mode, padding_mode, shards):
+    """ndconv_conv_fft_sharded_device: one conv_fft over an array that is already device-resident and row-partitioned.
+    shards[g] = dict(data=<device pointer of the first owned row>, rows=, halo_front=, halo_back=, out=<device pointer>); ghost rows
+    are filled peer-to-peer, the pipeline runs in place on every shard.  Enqueued only: synchronise the processors afterwards."""
+    lib = processors[0].lib
+    pr, keep = _global_problem(x_shape, dtype, kernel, conv_mode, padding_mode, lib)
+    arr = (_Shard * len(shards))()
+    for i, sh in enumerate(shards):
+        arr[i].data, arr[i].rows, arr[i].halo_front, arr[i].halo_back, arr[i].out = sh["data"], sh["rows"], sh["halo_front"], sh["halo_back"], sh["out"]
+    handles = (ctypes.c_void_p * len(processors))(*[p.handle for p in processors])
+    lib.check(lib.c.ndconv_conv_fft_sharded_device(handles, len(processors), ctypes.byref(pr), arr))
+    del keep
 
 
 class pinned:

@@ -439,6 +439,7 @@ static int try_direct_tile(ndconv_processor *p, const ndconv_problem *pr, const 
     case NDCONV_I16: case NDCONV_U16: st = launch_direct_tile<uint16_t>(p, tm, tp, grid, smem, alg_bytes); break;
     case NDCONV_I32: case NDCONV_U32: st = launch_direct_tile<uint32_t>(p, tm, tp, grid, smem, alg_bytes); break;
     case NDCONV_I64: case NDCONV_U64: st = launch_direct_tile<uint64_t>(p, tm, tp, grid, smem, alg_bytes); break;
+    case NDCONV_I128: case NDCONV_U128: st = launch_direct_tile<u128_t>(p, tm, tp, grid, smem, alg_bytes); break;
     case NDCONV_F32: st = launch_direct_tile<float>(p, tm, tp, grid, smem, alg_bytes); break;
     case NDCONV_F64: st = launch_direct_tile<double>(p, tm, tp, grid, smem, alg_bytes); break;
     case NDCONV_C32: st = launch_direct_tile<cx<float>>(p, tm, tp, grid, smem, alg_bytes); break;
@@ -490,6 +491,7 @@ static int conv_direct_impl(ndconv_processor *p, const ndconv_problem *pr, void 
     case NDCONV_I16: case NDCONV_U16: st = run_direct_t<uint16_t>(p, dp, alg_bytes); break;
     case NDCONV_I32: case NDCONV_U32: st = run_direct_t<uint32_t>(p, dp, alg_bytes); break;
     case NDCONV_I64: case NDCONV_U64: st = run_direct_t<uint64_t>(p, dp, alg_bytes); break;
+    case NDCONV_I128: case NDCONV_U128: st = run_direct_t<u128_t>(p, dp, alg_bytes); break;
     case NDCONV_F32: st = run_direct_t<float>(p, dp, alg_bytes); break;
     case NDCONV_F64: st = run_direct_t<double>(p, dp, alg_bytes); break;
     case NDCONV_C32: st = run_direct_t<cx<float>>(p, dp, alg_bytes); break;
@@ -777,6 +779,137 @@ int ndconv_conv_fft_sharded(ndconv_processor *const *handles, int n_handles, con
     }
 #endif
     return conv_fft_impl(handles[0], problem, out);
+}
+
+// ---- device-resident shards: ghost-row halo exchange + the unchanged single-GPU pipeline in place ----------------
+struct ShardGeom {
+    int64_t first_row = 0;              // global index of the first owned row
+    int64_t out_begin = 0, out_end = 0;
+    int64_t data_begin = 0, data_end = 0;   // global rows [begin, end) the slab problem holds (may run past [0, n) for a Circular axis 0)
+    int64_t pad_front = 0, pad_back = 0;    // explicit pads of the slab problem on axis 0 (non-zero only at a true, non-Circular array edge)
+};
+static int shard_geom(const ndconv_problem *problem, const Geom &g, int n_shards, const int64_t *shard_rows, int shard, ShardGeom *sg)
+{
+    if (!shard_rows || n_shards < 1 || shard < 0 || shard >= n_shards) { set_error("shard_plan: bad arguments"); return NDCONV_ERR_BAD_ARG; }
+    if (g.ndim < 2) { set_error("shard_plan: rank >= 2 (axis 0 is the sharded axis)"); return NDCONV_ERR_UNSUPPORTED; }
+    int64_t total = 0, first = 0;
+    for (int i = 0; i < n_shards; i++) { if (shard_rows[i] < 0) { set_error("shard_plan: negative row count"); return NDCONV_ERR_BAD_ARG; } if (i < shard) first += shard_rows[i]; total += shard_rows[i]; }
+    if (total != g.n[0]) { set_error("shard_plan: the shards' rows do not add up to data_shape[0]"); return NDCONV_ERR_BAD_ARG; }
+    ndconv_slab sl;
+    int st = slab_plan(g, n_shards, shard, &sl); if (st) return st;
+    sg->first_row = first; sg->out_begin = sl.out_begin; sg->out_end = sl.out_end;
+    if (sl.out_end <= sl.out_begin) { sg->data_begin = sg->data_end = first; return NDCONV_OK; }
+    const int64_t n = g.n[0], a = sl.pad_begin - g.pf[0], b = sl.pad_end - g.pf[0];       // un-padded coordinates of the rows the slab reads
+    const bool circ_f = problem->border[0][0].type == NDCONV_BORDER_CIRCULAR, circ_b = problem->border[0][1].type == NDCONV_BORDER_CIRCULAR;
+    sg->pad_front = (a < 0 && !circ_f) ? -a : 0;
+    sg->pad_back = (b > n && !circ_b) ? b - n : 0;
+    sg->data_begin = (a < 0 && !circ_f) ? 0 : a;
+    sg->data_end = (b > n && !circ_b) ? n : b;
+    if (sg->data_begin < -n || sg->data_end > 2 * n) { set_error("shard_plan: a Circular pad on axis 0 longer than the array is not sharded"); return NDCONV_ERR_UNSUPPORTED; }
+    return NDCONV_OK;
+}
+
+int ndconv_shard_plan(const ndconv_problem *problem, int n_shards, const int64_t *shard_rows, int shard, ndconv_shard_info *out)
+{
+    if (!out) { set_error("shard_plan: null output"); return NDCONV_ERR_BAD_ARG; }
+    memset(out, 0, sizeof(*out));
+    if (!problem) { set_error("shard_plan: null problem"); return NDCONV_ERR_BAD_ARG; }
+    ndconv_problem gp = *problem;                      // data pointer / strides / memory of the global problem are not used
+    if (!gp.data) gp.data = &gp;
+    Geom g; std::vector<int32_t> maps[NDC_MAX_DIM];
+    int st = check_problem(&gp, NDCONV_PATH_FFT, &g, maps); if (st) return st;
+    ShardGeom sg;
+    st = shard_geom(&gp, g, n_shards, shard_rows, shard, &sg); if (st) return st;
+    out->out_begin = sg.out_begin; out->out_end = sg.out_end; out->first_row = sg.first_row;
+    out->halo_front = std::max<int64_t>(0, sg.first_row - sg.data_begin);
+    out->halo_back = std::max<int64_t>(0, sg.data_end - (sg.first_row + shard_rows[shard]));
+    return NDCONV_OK;
+}
+
+int ndconv_conv_fft_sharded_device(ndconv_processor *const *handles, int n_handles, const ndconv_problem *problem, const ndconv_shard *shards)
+{
+    if (!handles || n_handles < 1 || !problem || !shards) { set_error("conv_fft_sharded_device: bad arguments"); return NDCONV_ERR_BAD_ARG; }
+    for (int i = 0; i < n_handles; i++) if (!handles[i]) { set_error("conv_fft_sharded_device: null processor"); return NDCONV_ERR_BAD_ARG; }
+    ndconv_problem gp = *problem;                      // the GLOBAL problem in standard layout; data pointer unused by the checks
+    gp.memory = NDCONV_MEM_DEVICE;
+    if (gp.ndim >= 1 && gp.ndim <= NDCONV_MAX_DIM) {
+        int64_t str = 1;
+        for (int a = gp.ndim - 1; a >= 0; a--) { gp.data_strides[a] = str; str *= gp.data_shape[a]; }
+    }
+    if (!gp.data) gp.data = shards[0].data;
+    Geom g; std::vector<int32_t> maps[NDC_MAX_DIM];
+    int st = check_problem(&gp, NDCONV_PATH_FFT, &g, maps); if (st) return st;
+    std::vector<int64_t> rows((size_t)n_handles), first((size_t)n_handles + 1, 0);
+    for (int i = 0; i < n_handles; i++) { rows[(size_t)i] = shards[i].rows; first[(size_t)i + 1] = first[(size_t)i] + shards[i].rows; }
+    std::vector<ShardGeom> sgs((size_t)n_handles);
+    for (int i = 0; i < n_handles; i++) {
+        st = shard_geom(&gp, g, n_handles, rows.data(), i, &sgs[(size_t)i]); if (st) return st;
+        const ShardGeom &sg = sgs[(size_t)i];
+        if (sg.out_end > sg.out_begin) {
+            if (!shards[i].data || !shards[i].out) { set_error("conv_fft_sharded_device: null shard pointer"); return NDCONV_ERR_BAD_ARG; }
+            if (sg.first_row - sg.data_begin > shards[i].halo_front || sg.data_end - first[(size_t)i + 1] > shards[i].halo_back) {
+                set_error("conv_fft_sharded_device: shard " + std::to_string(i) + " needs " + std::to_string(std::max<int64_t>(0, sg.first_row - sg.data_begin)) + " / " +
+                          std::to_string(std::max<int64_t>(0, sg.data_end - first[(size_t)i + 1])) + " ghost rows before / after its owned rows (ndconv_shard_plan)");
+                return NDCONV_ERR_BAD_ARG;
+            }
+        }
+    }
+#ifdef NDCONV_CUDA
+    const int64_t n = g.n[0];
+    const size_t row_bytes = (size_t)(g.data_total / n) * g.es;
+    // peer access once per ordered pair of distinct devices (without it cudaMemcpyPeerAsync stages through the host)
+    for (int i = 0; i < n_handles; i++)
+        for (int j = 0; j < n_handles; j++)
+            if (handles[i]->device != handles[j]->device) {
+                static std::mutex mu; static std::map<std::pair<int, int>, bool> done;
+                std::lock_guard<std::mutex> lk(mu);
+                auto key = std::make_pair(handles[i]->device, handles[j]->device);
+                if (!done.count(key)) {
+                    int can = 0;
+                    cudaDeviceCanAccessPeer(&can, key.first, key.second);
+                    if (can) { cudaSetDevice(key.first); if (cudaDeviceEnablePeerAccess(key.second, 0) != cudaSuccess) cudaGetLastError(); }
+                    done[key] = true;
+                }
+            }
+    std::vector<int> status((size_t)n_handles, NDCONV_OK);
+    std::vector<std::string> message((size_t)n_handles);
+    auto work = [&](int i) -> int {
+        const ShardGeom &sg = sgs[(size_t)i];
+        if (sg.out_end <= sg.out_begin) return (int)NDCONV_OK;
+        ndconv_processor *p = handles[i];
+        int s2 = set_device(p); if (s2) return s2;
+        unsigned char *own = (unsigned char *)shards[i].data;
+        // ghost rows: global rows [data_begin, first) and [first + rows, data_end), taken modulo n (Circular), from whoever owns them
+        auto fetch = [&](int64_t lo, int64_t hi) -> int {
+            for (int64_t r = lo; r < hi;) {
+                const int64_t m = ((r % n) + n) % n;
+                int o = (int)(std::upper_bound(first.begin(), first.end(), m) - first.begin()) - 1;
+                const int64_t cnt = std::min(hi - r, first[(size_t)o + 1] - m);
+                const unsigned char *src = (const unsigned char *)shards[o].data + (size_t)(m - first[(size_t)o]) * row_bytes;
+                unsigned char *dst = own + (r - sg.first_row) * (int64_t)row_bytes;
+                CU_CHECK(cudaMemcpyPeerAsync(dst, p->device, src, handles[o]->device, (size_t)cnt * row_bytes, p->stream));
+                r += cnt;
+            }
+            return NDCONV_OK;
+        };
+        s2 = fetch(sg.data_begin, std::min(sg.first_row, sg.data_end)); if (s2) return s2;
+        s2 = fetch(std::max(first[(size_t)i + 1], sg.data_begin), sg.data_end); if (s2) return s2;
+        ndconv_problem sp = gp;
+        sp.data = own + (sg.data_begin - sg.first_row) * (int64_t)row_bytes;
+        sp.data_shape[0] = sg.data_end - sg.data_begin;
+        sp.pad[0][0] = sg.pad_front; sp.pad[0][1] = sg.pad_back;
+        return conv_fft_impl(p, &sp, shards[i].out);
+    };
+    if (n_handles == 1) { st = work(0); return st; }
+    std::vector<std::thread> workers;
+    for (int i = 0; i < n_handles; i++) workers.emplace_back([&, i]() { status[(size_t)i] = work(i); if (status[(size_t)i]) message[(size_t)i] = get_error(); });
+    for (auto &w : workers) w.join();
+    for (int i = 0; i < n_handles; i++) if (status[(size_t)i]) { set_error(message[(size_t)i]); return status[(size_t)i]; }
+    return NDCONV_OK;
+#else
+    set_error("conv_fft_sharded_device: device memory needs the CUDA build");
+    return NDCONV_ERR_CUDA;
+#endif
 }
 
 // Independent convolutions distributed whole (north star: "batched independent convolutions are distributed whole"):

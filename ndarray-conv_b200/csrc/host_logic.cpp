@@ -17,7 +17,7 @@ size_t dtype_size(int dtype)
     switch (dtype) {
     case NDCONV_I32: case NDCONV_F32: case NDCONV_U32: return 4;
     case NDCONV_I64: case NDCONV_F64: case NDCONV_C32: case NDCONV_U64: return 8;
-    case NDCONV_C64: return 16;
+    case NDCONV_C64: case NDCONV_I128: case NDCONV_U128: return 16;
     case NDCONV_I8: case NDCONV_U8: return 1;
     case NDCONV_I16: case NDCONV_U16: return 2;
     }

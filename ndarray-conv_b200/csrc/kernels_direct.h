@@ -23,6 +23,12 @@ NDC_INT_ELEM(uint16_t)
 NDC_INT_ELEM(uint32_t)
 NDC_INT_ELEM(uint64_t)
 #undef NDC_INT_ELEM
+// i128 / u128 (T: NumAssign + Copy admits them, src/conv/mod.rs:118-121): two 64-bit halves, wrapping multiply-add
+typedef unsigned __int128 u128_t;
+template <> struct Elem<u128_t> {
+    static HD u128_t zero() { return (u128_t)0; }
+    static HD u128_t mac(u128_t acc, u128_t a, u128_t w) { return acc + a * w; }
+};
 
 HD float f_mul(float a, float b)
 {

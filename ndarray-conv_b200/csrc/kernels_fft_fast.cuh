@@ -24,6 +24,7 @@
 #include "packed_cf.cuh"
 
 #ifdef NDCONV_CUDA
+#include <cuda.h>          // CUtensorMap (col_pass_tma)
 namespace ndc {
 namespace fast {
 
@@ -819,31 +820,28 @@ struct ColParams {
     int64_t tile_elems, ntiles_total;
     int64_t nwork;          // ntiles_total * outer * inner / 8
     int skip;               // modes 1 / 2: the first `skip` rows of the axis (= Kd - 1, the aliased head the crop discards) are not stored
+    int store_rows;         // col_pass_tma: rows per store box (divides F - skip)
 };
 
-// EARLY (experiment, NDCONV_COL_EARLY=1, not yet measured): a half-item staging buffer of its own (rows [0, F/2) of the next item)
-// that is free as soon as the registers are loaded, so half of the next item is prefetched at the START of an item instead of
-// just before the last butterfly; rows [F/2, F) are staged late into the exchange buffer as in the default kernel.
-template <int E, int Tc, bool EARLY = false> struct ColCfg {
+template <int E, int Tc> struct ColCfg {
     static constexpr int F = E * Tc, Mc = E / Tc;
     static constexpr int threads = Tc * 8;
     static constexpr int pitch = Tc * 8 + 8;                             // padded k1-row stride of the exchange buffer
     static constexpr int ex = (E * pitch > F * 8 ? E * pitch : F * 8);
-    static constexpr int smem = ((Tc == E ? 1 : 2) * F + ex + (EARLY ? F * 4 : 0)) * 8;   // forward table, transposed table for the inverse when Tc != E, exchange buffer, half-item buffer
+    static constexpr int smem = ((Tc == E ? 1 : 2) * F + ex) * 8;   // forward table, transposed table for the inverse when Tc != E, exchange buffer
     static constexpr int min_blocks = (E == 32 && Tc == 32) ? 2 : 4;      // 512-row tiles: 4 CTAs of 128 threads at 126 registers beat 3 at 168 (s512: 52 -> 48 us)
 };
 
-template <int E, int Tc, bool EARLY = false>
-__global__ void __launch_bounds__(ColCfg<E, Tc, EARLY>::threads, ColCfg<E, Tc, EARLY>::min_blocks) col_pass(const __grid_constant__ ColParams p)
+template <int E, int Tc>
+__global__ void __launch_bounds__(ColCfg<E, Tc>::threads, ColCfg<E, Tc>::min_blocks) col_pass(const __grid_constant__ ColParams p)
 {
     pdl_launch_dependents();
-    using C = ColCfg<E, Tc, EARLY>;
+    using C = ColCfg<E, Tc>;
     constexpr int F = C::F, Mc = C::Mc, pitch = C::pitch;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     pc *s_tw = reinterpret_cast<pc *>(smem_raw);        // s_tw[k1 * Tc + i] = W_F^{i k1}, k1 < E, i < Tc   (forward: i is the thread index)
     pc *s_twT = s_tw + F;                               // s_twT[ii * E + k1] = W_F^{ii k1}   (inverse, Tc != E: k1 is the thread-dependent index)
     pc *S = s_tw + (Tc == E ? 1 : 2) * F;
-    [[maybe_unused]] pc *S2 = S + C::ex;                // EARLY: rows [0, F/2) of the staged item, S2[row * 8 + column]
     const int tid = threadIdx.x;
     const int c = tid & 7, i = tid >> 3;                // column of the block, thread index inside the column (< Tc)
     for (int idx = tid; idx < F; idx += C::threads) { s_tw[idx] = ld_pc(p.tw + (idx / Tc) * (idx % Tc)); if (Tc != E) s_twT[idx] = ld_pc(p.tw + (idx / E) * (idx % E)); }
@@ -867,22 +865,11 @@ __global__ void __launch_bounds__(ColCfg<E, Tc, EARLY>::threads, ColCfg<E, Tc, E
         }
         cp_async_commit();
     };
-    // EARLY: the two halves of an item, staged separately (rows < F/2 -> S2, rows >= F/2 -> their usual place in S)
-    constexpr int kHalfChunks = (F * 2 + C::threads - 1) / C::threads;
-    [[maybe_unused]] auto prefetch_half = [&](const Item &it, bool hi) {
-        const cf *gn = p.ws + it.off;
-#pragma unroll
-        for (int m = 0; m < kHalfChunks; m++) {
-            const int id = tid + C::threads * m, row = (id >> 2) + (hi ? F / 2 : 0), part = id & 3;
-            if (F * 2 % C::threads == 0 || id < F * 2) cp_async16((hi ? S : S2) + row * 8 + part * 2, gn + (int64_t)row * p.inner + part * 2);
-        }
-        cp_async_commit();
-    };
     pdl_wait();                                      // before the first access to the workspace (the table staging above reads constants)
     Item nxt; nxt.off = 0; nxt.rel = 0;
     if ((int64_t)blockIdx.x < p.nwork) {
         nxt = decode(blockIdx.x);
-        if constexpr (EARLY) { prefetch_half(nxt, false); prefetch_half(nxt, true); } else prefetch(nxt);
+        prefetch(nxt);
     }
     for (int64_t w = blockIdx.x; w < p.nwork; w += gridDim.x) {
         const Item cur = nxt;
@@ -893,9 +880,8 @@ __global__ void __launch_bounds__(ColCfg<E, Tc, EARLY>::threads, ColCfg<E, Tc, E
         if (p.mode != 1) {
             // ---- forward: rows i + Tc j -> radix E -> twiddle -> exchange -> radix Tc -> rows q = (i + Tc m) + E k2 ----
 #pragma unroll
-            for (int j = 0; j < E; j++) v[j] = ((EARLY && j < E / 2) ? S2 : S)[(i + Tc * j) * 8 + c];      // row i + Tc j < F/2 <=> j < E/2
+            for (int j = 0; j < E; j++) v[j] = S[(i + Tc * j) * 8 + c];
             __syncthreads();
-            if constexpr (EARLY) { if (w + gridDim.x < p.nwork) { nxt = decode(w + gridDim.x); prefetch_half(nxt, false); } }   // S2 is free: first half of the next item
             pk::dft<false, E>(v);
 #pragma unroll
             for (int k1 = 0; k1 < E; k1++) S[k1 * pitch + i * 8 + c] = pk::cmul(v[k1], s_tw[k1 * Tc + i]);
@@ -917,11 +903,11 @@ __global__ void __launch_bounds__(ColCfg<E, Tc, EARLY>::threads, ColCfg<E, Tc, E
 #pragma unroll
             for (int m = 0; m < Mc; m++)
 #pragma unroll
-                for (int k2 = 0; k2 < Tc; k2++) v[m * Tc + k2] = ((EARLY && k2 < Tc / 2) ? S2 : S)[(i + Tc * m + E * k2) * 8 + c];   // row < F/2 <=> k2 < Tc/2
+                for (int k2 = 0; k2 < Tc; k2++) v[m * Tc + k2] = S[(i + Tc * m + E * k2) * 8 + c];
         }
         if (p.mode == 0) {
             __syncthreads();                               // all exchange reads done: S may be restaged
-            if (w + gridDim.x < p.nwork) { if constexpr (EARLY) prefetch_half(nxt, true); else { nxt = decode(w + gridDim.x); prefetch(nxt); } }
+            if (w + gridDim.x < p.nwork) { nxt = decode(w + gridDim.x); prefetch(nxt); }
 #pragma unroll
             for (int m = 0; m < Mc; m++)
 #pragma unroll
@@ -933,7 +919,6 @@ __global__ void __launch_bounds__(ColCfg<E, Tc, EARLY>::threads, ColCfg<E, Tc, E
             // so the inverse is the forward flow with conjugated twiddles (no transposed table needed)
             pk::dft<true, E>(v);
             __syncthreads();                               // every thread has finished reading S
-            if constexpr (EARLY) { if (p.mode == 1 && w + gridDim.x < p.nwork) { nxt = decode(w + gridDim.x); prefetch_half(nxt, false); } }
 #pragma unroll
             for (int n1 = 0; n1 < E; n1++) S[n1 * pitch + i * 8 + c] = pk::cmulc(v[n1], s_tw[n1 * Tc + i]);
             __syncthreads();
@@ -945,7 +930,6 @@ __global__ void __launch_bounds__(ColCfg<E, Tc, EARLY>::threads, ColCfg<E, Tc, E
 #pragma unroll
             for (int m = 0; m < Mc; m++) pk::dft<true, Tc>(v + m * Tc);
             __syncthreads();                               // every thread has finished reading S
-            if constexpr (EARLY) { if (p.mode == 1 && w + gridDim.x < p.nwork) { nxt = decode(w + gridDim.x); prefetch_half(nxt, false); } }
 #pragma unroll
             for (int m = 0; m < Mc; m++)
 #pragma unroll
@@ -956,11 +940,157 @@ __global__ void __launch_bounds__(ColCfg<E, Tc, EARLY>::threads, ColCfg<E, Tc, E
             for (int k1 = 0; k1 < E; k1++) v[k1] = S[k1 * pitch + i * 8 + c];
             __syncthreads();
         }
-        if (w + gridDim.x < p.nwork) { if constexpr (EARLY) prefetch_half(nxt, true); else { nxt = decode(w + gridDim.x); prefetch(nxt); } }
+        if (w + gridDim.x < p.nwork) { nxt = decode(w + gridDim.x); prefetch(nxt); }
         pk::dft<true, E>(v);
 #pragma unroll
         for (int j = 0; j < E; j++) if (i + Tc * j >= p.skip) st_pc(gt + (int64_t)(i + Tc * j) * p.inner, v[j]);
     }
+}
+
+// ---- column pass, F = 1024, TMA-fed: one CTA per SM, two compute groups ----------------------------------------------------------
+// col_pass above runs two CTAs per SM and stages the next item into its exchange buffer with cp.async, which is free only late in
+// an item: the load latency of every item is exposed, 16 LDGSTS + 32 STG per thread carry 64-bit address arithmetic, and the
+// register file (2 x 256 threads x 128) leaves no room for a third CTA.  col_pass_tma keeps the same butterflies but restructures
+// the data movement around the TMA unit:
+//   * ONE CTA of 512 threads per SM = two independent compute groups of 256 threads (named barriers 1 / 2), one twiddle table;
+//   * a landing buffer P (64 KB) that `cp.async.bulk.tensor.2d` box loads (4 x [256 rows x 64 B]) fill while BOTH groups compute:
+//     the group that has just drained P into registers immediately issues the load of the item the OTHER group takes next, so a full
+//     item of look-ahead is always in flight and no thread ever waits for a load it has just issued;
+//   * results leave through the group's (then idle) exchange buffer as dense [row][64 B] boxes and `cp.async.bulk.tensor.2d` stores
+//     (rows [skip, F) only: the aliased head rows the crop discards are never written);
+//   * no per-thread global address arithmetic for the workspace at all (SASS: UTMALDG / UTMASTG, mbarrier SYNCS).
+// Shared memory: P 64 KB + 2 x 66 KB exchange + 8 KB twiddles = 204 KB.
+struct ColTmaCfg {
+    static constexpr int E = 32, Tc = 32, F = 1024, pitch = Tc * 8 + 8;
+    static constexpr int group = 256, threads = 512;
+    static constexpr int p_elems = F * 8, x_elems = E * pitch;                     // 8192, 8448 complex
+    static constexpr int smem = (p_elems + 2 * x_elems + F) * 8 + 64 + 128;         // + mbarriers + alignment slack
+    static constexpr int box_rows = 256;
+};
+
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bar_group(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(ColTmaCfg::group) : "memory"); }
+__device__ __forceinline__ void mbar_wait(uint32_t mb, uint32_t parity)
+{
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(mb), "r"(parity) : "memory");
+    }
+}
+__device__ __forceinline__ pc lds_pc(uint32_t a) { pc r; asm volatile("ld.shared.b64 %0, [%1];" : "=l"(r.v) : "r"(a)); return r; }
+__device__ __forceinline__ void sts_pc(uint32_t a, pc v) { asm volatile("st.shared.b64 [%0], %1;" ::"r"(a), "l"(v.v) : "memory"); }
+
+// INNER > 0: the row pitch of the tile (complex elements) as a compile-time constant, so the kernel-spectrum loads address with
+// immediates (1032 = the 2048-sample last-axis tile of the BASELINE workload); 0: read it from the parameters.
+template <int INNER, bool TMA_STORE = true>
+__global__ void __launch_bounds__(ColTmaCfg::threads, 1)
+col_pass_tma(const __grid_constant__ ColParams p, const __grid_constant__ CUtensorMap tm_ld, const __grid_constant__ CUtensorMap tm_st)
+{
+    pdl_launch_dependents();
+    using C = ColTmaCfg;
+    constexpr int E = C::E, Tc = C::Tc, F = C::F, pitch = C::pitch;
+    extern __shared__ __align__(128) unsigned char smem_dyn[];
+    unsigned char *base = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 127) & ~(uintptr_t)127);
+    const int tid = threadIdx.x, g = tid >> 8, lt = tid & 255;
+    const int c = lt & 7, i = lt >> 3;                       // column of the block, thread index inside the column (< 32)
+    const uint32_t sP = smem_addr(base);
+    const uint32_t sX = sP + C::p_elems * 8 + g * (C::x_elems * 8);
+    pc *s_tw = reinterpret_cast<pc *>(base + (C::p_elems + 2 * C::x_elems) * 8);      // s_tw[k1 * 32 + i] = W_F^{i k1}
+    const uint32_t sT = sP + (C::p_elems + 2 * C::x_elems) * 8 + i * 8;               // this thread's column of the table
+    const uint32_t mb0 = sP + (C::p_elems + 2 * C::x_elems + F) * 8;                   // full[0], full[1]: P holds an item for group 0 / 1
+    const uint32_t mbg = mb0 + 8 * g;
+    for (int idx = tid; idx < F; idx += C::threads) s_tw[idx] = ld_pc(p.tw + (idx >> 5) * (idx & 31));
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb0));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb0 + 8));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    const int64_t inner = INNER > 0 ? (int64_t)INNER : p.inner;
+    const uint32_t iblocks = (uint32_t)(inner / 8), outer = (uint32_t)p.outer;
+    // item w -> (q = tile * outer + o, 8-column block ib): rows [q F, q F + F) x columns [8 ib, 8 ib + 8) of the workspace seen as
+    // one 2-D array of `inner` columns
+    auto issue_load = [&](int64_t w, int gi) {
+        const uint32_t w32 = (uint32_t)w, q = w32 / iblocks, ib = w32 - q * iblocks;
+        const uint32_t mb = mb0 + 8 * gi;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"((uint32_t)(C::p_elems * 8)) : "memory");
+#pragma unroll
+        for (int b = 0; b < F / C::box_rows; b++)
+            asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                         ::"r"(sP + b * C::box_rows * 64), "l"(reinterpret_cast<uint64_t>(&tm_ld)), "r"((int)(ib * 8)), "r"((int)(q * F + b * C::box_rows)), "r"(mb)
+                         : "memory");
+    };
+    const uint64_t pol_keep = l2_policy_evict_last();
+    pdl_wait();                                      // before the first access to the workspace
+    if (tid == 0 && (int64_t)blockIdx.x < p.nwork) issue_load(blockIdx.x, 0);
+    uint32_t parity = 0;
+    const int nst = (F - p.skip) / p.store_rows;     // store boxes per item (host: store_rows divides F - skip; skip and store_rows even)
+    for (int64_t n = g;; n += 2) {
+        const int64_t w = (int64_t)blockIdx.x + n * gridDim.x;
+        if (w >= p.nwork) break;
+        const uint32_t w32 = (uint32_t)w, q = w32 / iblocks, ib = w32 - q * iblocks;
+        pc v[32];
+        mbar_wait(mbg, parity);
+        parity ^= 1;
+#pragma unroll
+        for (int j = 0; j < 32; j++) v[j] = lds_pc(sP + ((i + 32 * j) * 8 + c) * 8);          // rows i + 32 j (both the forward's and, square case, the inverse's start)
+        if (TMA_STORE && lt == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the previous item's stores have read the exchange buffer
+        // The first butterfly CONSUMES every loaded value before the barrier: a thread may arrive at a barrier with its shared-memory
+        // loads still queued, and the TMA load issued after the barrier would overwrite P under them (seen on workspaces that fit
+        // L2, where the box arrives within a few hundred cycles: the last rows of an item came out as the next item's).
+        if (p.mode != 1) pk::dft<false, E>(v); else pk::dft<true, E>(v);
+        bar_group(1 + g);
+        if (lt == 0 && w + gridDim.x < p.nwork) issue_load(w + gridDim.x, g ^ 1);             // P is drained: the other group's next item
+        if (p.mode != 1) {
+#pragma unroll
+            for (int k1 = 0; k1 < E; k1++) sts_pc(sX + (k1 * pitch + i * 8 + c) * 8, pk::cmul(v[k1], lds_pc(sT + k1 * Tc * 8)));
+            bar_group(1 + g);
+#pragma unroll
+            for (int ii = 0; ii < Tc; ii++) v[ii] = lds_pc(sX + (i * pitch + ii * 8 + c) * 8);
+            pk::dft<false, Tc>(v);                                                              // v[k2] = row i + 32 k2
+            if (p.mode == 2) {
+                const uint32_t o = q % outer;
+                const cf *kp = p.kspec + ((int64_t)o * F * inner + ib * 8 + c) + (int64_t)i * inner;
+#pragma unroll
+                for (int k2 = 0; k2 < Tc; k2++) v[k2] = pk::cmul(v[k2], ld_pc_keep(kp + (int64_t)(E * k2) * inner, pol_keep));
+                pk::dft<true, E>(v);
+                bar_group(1 + g);                          // every thread has finished reading the exchange buffer
+            }
+        }
+        if (p.mode != 0) {
+            // square case: the rows this thread holds (i + 32 k2) are the rows the forward-structured flow starts from, so the
+            // inverse is the forward flow with conjugated twiddles (mode INV: its first butterfly ran before the barrier above)
+#pragma unroll
+            for (int n1 = 0; n1 < E; n1++) sts_pc(sX + (n1 * pitch + i * 8 + c) * 8, pk::cmulc(v[n1], lds_pc(sT + n1 * Tc * 8)));
+            bar_group(1 + g);
+#pragma unroll
+            for (int ii = 0; ii < Tc; ii++) v[ii] = lds_pc(sX + (i * pitch + ii * 8 + c) * 8);
+            pk::dft<true, E>(v);                           // v[j] = row i + 32 j
+        }
+        if constexpr (!TMA_STORE) {
+            // A/B variant (NDCONV_COL_STG): results leave straight from the registers, 64-byte row segments per 8 lanes
+            cf *gt = p.ws + ((int64_t)q * F + i) * inner + ib * 8 + c;
+#pragma unroll
+            for (int j = 0; j < 32; j++) if (i + 32 * j >= p.skip) st_pc(gt + (int64_t)(32 * j) * inner, v[j]);
+            continue;                                      // (the exchange reads were consumed by the last butterfly; the next item's first barrier orders its writes)
+        }
+        bar_group(1 + g);                                  // exchange reads done: the buffer becomes the dense [row][8] store staging
+#pragma unroll
+        for (int j = 0; j < 32; j++) sts_pc(sX + ((i + 32 * j) * 8 + c) * 8, v[j]);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        bar_group(1 + g);
+        if (lt == 0) {
+            for (int b = 0; b < nst; b++) {
+                const int r = p.skip + b * p.store_rows;
+                asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+                             ::"l"(reinterpret_cast<uint64_t>(&tm_st)), "r"((int)(ib * 8)), "r"((int)(q * F + r)), "r"(sX + r * 64) : "memory");
+            }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+    }
+    if (lt == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 }  // namespace fast

@@ -33,14 +33,14 @@ enum { ORC_MODE_FULL = 0, ORC_MODE_SAME = 1, ORC_MODE_VALID = 2, ORC_MODE_CUSTOM
 enum { ORC_B_ZEROS = 0, ORC_B_CONST = 1, ORC_B_REFLECT = 2, ORC_B_REPLICATE = 3, ORC_B_CIRCULAR = 4 };
 /* element types */
 enum { ORC_I32 = 0, ORC_I64 = 1, ORC_F32 = 2, ORC_F64 = 3, ORC_C32 = 4, ORC_C64 = 5,
-       ORC_I8 = 6, ORC_I16 = 7, ORC_U8 = 8, ORC_U16 = 9, ORC_U32 = 10, ORC_U64 = 11 };
+       ORC_I8 = 6, ORC_I16 = 7, ORC_U8 = 8, ORC_U16 = 9, ORC_U32 = 10, ORC_U64 = 11, ORC_I128 = 12, ORC_U128 = 13 };
 
 int orc_elem_size(int dtype)
 {
     switch (dtype) {
     case ORC_I32: case ORC_F32: case ORC_U32: return 4;
     case ORC_I64: case ORC_F64: case ORC_C32: case ORC_U64: return 8;
-    case ORC_C64: return 16;
+    case ORC_C64: case ORC_I128: case ORC_U128: return 16;
     case ORC_I8: case ORC_U8: return 1;
     case ORC_I16: case ORC_U16: return 2;
     }
@@ -372,6 +372,7 @@ int orc_conv_direct(int dtype, int ndim, const void *data, const int64_t *nshape
         switch (dtype) {
         case ORC_I32: case ORC_U32: MAC_LOOP(uint32_t, 0u, acc += a * w) break;
         case ORC_I64: case ORC_U64: MAC_LOOP(uint64_t, 0ull, acc += a * w) break;
+        case ORC_I128: case ORC_U128: MAC_LOOP(unsigned __int128, 0, acc += a * w) break;   /* i128 / u128: wrapping, as every integer type */
         case ORC_I8: case ORC_U8: MAC_LOOP(uint8_t, 0, acc = (uint8_t)(acc + (uint8_t)(a * w))) break;
         case ORC_I16: case ORC_U16: MAC_LOOP(uint16_t, 0, acc = (uint16_t)(acc + (uint16_t)(a * w))) break;
         case ORC_F32: MAC_LOOP(float, 0.0f, acc += a * w) break;

@@ -38,6 +38,7 @@ _DTYPES = {
     np.dtype(np.int32): 0, np.dtype(np.int64): 1, np.dtype(np.float32): 2, np.dtype(np.float64): 3,
     np.dtype(np.complex64): 4, np.dtype(np.complex128): 5, np.dtype(np.int8): 6, np.dtype(np.int16): 7,
     np.dtype(np.uint8): 8, np.dtype(np.uint16): 9, np.dtype(np.uint32): 10, np.dtype(np.uint64): 11,
+    np.dtype([("lo", "<u8"), ("hi", "<i8")]): 12, np.dtype([("lo", "<u8"), ("hi", "<u8")]): 13,     # Rust i128 / u128 as (lo, hi) records
 }
 _BORDER = {"zeros": 0, "const": 1, "reflect": 2, "replicate": 3, "circular": 4}
 _MODE = {"full": 0, "same": 1, "valid": 2, "custom": 3, "explicit": 4}
@@ -122,6 +123,15 @@ def lower_padding(padding, ndim, dtype):
         return _BORDER[b[0]], b[1]
     codes = np.zeros((ndim, 2), np.int32)
     vals = np.zeros((ndim, 2), dtype)
+    if np.dtype(dtype).names:                       # i128 / u128 records: constants are Python ints
+        def one(b, _one=one):                       # noqa: F811
+            c, v = _one(b)
+            u = int(v) % (1 << 128)
+            rec = np.zeros((), dtype)
+            rec["lo"] = u & ((1 << 64) - 1)
+            h = u >> 64
+            rec["hi"] = h - (1 << 64) if (np.dtype(dtype)["hi"].kind == "i" and h >= (1 << 63)) else h
+            return c, rec
     if isinstance(padding, str) or padding[0] == "const":
         c, v = one(padding)
         codes[:] = c

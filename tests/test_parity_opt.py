@@ -1,4 +1,4 @@
-"""sm_100a fast path (kernels_fft_opt.cuh: 2-D real f32, 1024 x 2048 overlap-save tiles) against the CPU oracle.
+"""sm_100a fast path (kernels_fft_fast.cuh: real f32 / Complex<f32>, rank 1-3, power-of-two overlap-save tiles) against the CPU oracle.
 Device-only kernels (warp shuffles): these tests need a B200."""
 import numpy as np
 import pytest
@@ -35,6 +35,10 @@ CASES = [
     ((1100, 4000), (5, 9), 2, "full", ("custom", [("const", 0.75), "circular"]), True),
     ((1100, 4000), (5, 9), 1, "same", ("custom", ["circular", "reflect"]), True),             # Circular on axis 0: never split
     ((600, 40, 300), (5, 3, 3), 1, "same", ("const", 0.25), True),                             # rank 3
+    # 1024-row column tiles outside the 2-D case (col_pass_tma, modes FWD / INV, outer > 1, row pitch != 1032)
+    ((3, 1000, 300), (2, 3, 5), 1, "same", "reflect", True),                                   # middle axis: forward and inverse passes of their own
+    ((1000, 20, 300), (3, 3, 3), 1, "full", ("custom", ["replicate", "circular", "zeros"]), False),   # axis 0 with a [F1][pitch] inner extent
+    ((1000, 1500), (4, 4), 1, "same", "zeros", True),                                          # even Kd: odd number of aliased head rows
     # rank 1: fast::row1d, the whole pipeline in one launch (tiles of 256 .. 2048 samples)
     ((5000,), (31,), 1, "same", "zeros", True),                                                # BASELINE configs[0]
     ((700,), (5,), 1, "full", "reflect", True),
