@@ -479,6 +479,12 @@ def other_shapes(pkg, lib, proc, dev, stream):
          pkg.ConvMode.Custom([1, 2, 2], [2, 2, 2]), pkg.PaddingMode.Replicate),
         # not a BASELINE config: a large 1-D problem, where the rank-1 kernel is a single pass over memory (8 B per sample)
         ("extra 1D f32 x=67108864 k=63 Full Reflect", "fft", np.float32, (1 << 26,), (63,), 1, pkg.ConvMode.Full, pkg.PaddingMode.Reflect),
+        # same-shape batches: a leading axis of kernel extent 1 is folded into one launch per pass (us_per_call / 64 = per problem)
+        ("c2 x64 stacked: x=(64,200,5000) k=(1,11,31) dil (1,2,2) Same [Zeros,Reflect,Circular]", "fft", np.float32, (64, 200, 5000), (1, 11, 31), [1, 2, 2], pkg.ConvMode.Same,
+         pkg.PaddingMode.Custom([B.Zeros, B.Reflect, B.Circular])),
+        ("c3 x64 stacked: x=(64,10,100,200) k=(1,5,11,31) Same Zeros", "fft", np.float32, (64, 10, 100, 200), (1, 5, 11, 31), 1, pkg.ConvMode.Same, pkg.PaddingMode.Zeros),
+        # the direct kernel in the throughput regime (not a BASELINE config): 75 multiply-adds per output make it ALU / shared-memory bound
+        ("extra 3D direct conv i32 x=(256,1024,1024) k=(3,5,5) Same Replicate", "direct", np.int32, (256, 1024, 1024), (3, 5, 5), 1, pkg.ConvMode.Same, pkg.PaddingMode.Replicate),
     ]
     out = []
     for ci, (name, path, dt, xs, ks, dil, mode, pm) in enumerate(cfgs):
@@ -521,7 +527,14 @@ def other_shapes(pkg, lib, proc, dev, stream):
             call()
         kp = read_profile(lib, proc)
         lib.c.ndconv_processor_set_profiling(proc.handle, 0)
-        out.append({"shape": name, "us_per_call": us, "Gsamples_per_s": n_out / us / 1e3, "launches_per_call": nl,
+        extra = {}
+        if "stacked" in name:
+            extra["us_per_problem"] = us / xs[0]
+        if path == "direct":
+            taps = int(np.count_nonzero(kh))
+            extra["taps"] = taps
+            extra["GMAC_per_s"] = n_out * taps / us / 1e3
+        out.append({"shape": name, **extra, "us_per_call": us, "Gsamples_per_s": n_out / us / 1e3, "launches_per_call": nl,
                     "compulsory_GBps": (xh.nbytes + kh.nbytes + n_out * xh.itemsize) / us / 1e3,
                     "kernel_us_per_call": {k["kernel"]: round(k["total_ms"] * 1e3 / 10, 2) for k in kp},
                     "note": "device-resident, warm processor, includes host-side planning of every call"})

@@ -107,7 +107,8 @@ static void fast_pick_tile(int64_t P, int64_t Kd, const int *menu, int nmenu, Ax
     }
 }
 
-static int make_plan(const Geom &g, FftPlan *pl)
+// `batch`: same-shape problems that share every launch (conv_fft_same_shape_batch) -- the small-problem tile rule looks at the whole stack
+static int make_plan(const Geom &g, FftPlan *pl, int64_t batch = 1)
 {
     const int N = g.ndim;
     const bool is_cx = dtype_is_complex(g.dtype), is_dbl = (g.dtype == NDCONV_F64 || g.dtype == NDCONV_C64);
@@ -123,7 +124,7 @@ static int make_plan(const Geom &g, FftPlan *pl)
             // NDCONV_TILE_SLACK=<percent> (negative: off) and NDCONV_TILE_SMALL_K=<thousand samples> override for experiments
             static const double slack_env = getenv("NDCONV_TILE_SLACK") ? atof(getenv("NDCONV_TILE_SLACK")) / 100.0 : 0.10;
             static const double small_k = getenv("NDCONV_TILE_SMALL_K") ? atof(getenv("NDCONV_TILE_SMALL_K")) : 1280.0;
-            double tot = 1; for (int b = 0; b < N; b++) tot *= (double)g.P[b];
+            double tot = (double)batch; for (int b = 0; b < N; b++) tot *= (double)g.P[b];
             const double slack = tot < small_k * 1000.0 ? slack_env : -1.0;
             if (a == N - 1) fast_pick_tile(g.P[a], g.Kd[a], is_cx ? menu_last_cx : menu_last, 4, &pl->tl[a], slack);
             else fast_pick_tile(g.P[a], g.Kd[a], menu_col, 7, &pl->tl[a], slack);
@@ -242,7 +243,7 @@ static int get_plan_entry(ndconv_processor *p, const ndconv_problem *pr, int pat
         push(hdr, sizeof(hdr));
         for (int a = 0; a < N; a++) {
             int64_t v[9] = {pr->data_shape[a], pr->data_strides[a], pr->kernel_shape[a], pr->kernel_strides[a], pr->dilation[a],
-                            pr->pad[a][0], pr->pad[a][1], pr->stride[a], 0};
+                            pr->pad[a][0], pr->pad[a][1], pr->stride[a], a == 0 ? p->batch_n : 0};
             push(v, sizeof(v));
             push(&pr->border[a][0].type, 4); push(pr->border[a][0].value, 16);
             push(&pr->border[a][1].type, 4); push(pr->border[a][1].value, 16);
@@ -280,7 +281,7 @@ static int get_plan_entry(ndconv_processor *p, const ndconv_problem *pr, int pat
         ent->ntap = taps.ntap;
         st = upload_meta(p, ent->meta, g, maps, &taps, &ent->ml); if (st) return st;
     } else {
-        st = make_plan(g, &ent->pl); if (st) return st;
+        st = make_plan(g, &ent->pl, p->batch_n); if (st) return st;
         plan_axis0_split(pr, g, ent->pl, ent.get());
         st = upload_meta(p, ent->meta, g, maps, nullptr, &ent->ml); if (st) return st;
     }

@@ -77,6 +77,9 @@ struct RowParams {
     const cf *kfast;                           // rank 1 only: the kernel spectrum of one tile in the workspace row layout
     int64_t nwork;                             // rows to transform (fwd) / (output row, tile) pairs (inv) / tiles (rank 1)
     int64_t rows_per_tile, tile_elems;         // prod of the outer F ; rows_per_tile * (L + 8)
+    // same-shape batch (a leading axis of kernel extent 1 folded away by the host): problem b reads x + b * xstr_batch, its tiles follow
+    // those of problem b - 1 in the workspace and its output rows follow in `out`; the batch index is the outermost tile coordinate
+    int64_t xstr_batch;
 };
 
 // ---- row forward ---------------------------------------------------------------------------------------------------------
@@ -117,6 +120,7 @@ template <int N> __device__ __forceinline__ RowSrcInfo resolve_fwd_row(const Row
         if (c[a] >= p.P[a]) r.beyond = true;
     }
     if (r.beyond) return r;
+    r.base = (int64_t)tt * p.xstr_batch;         // what is left of the tile index is the batch index (0 without a batch)
 #pragma unroll
     for (int a = N - 2; a >= 0; a--) {
         if (r.has_const) continue;
@@ -257,7 +261,7 @@ template <int N> __device__ __forceinline__ RowInvInfo resolve_inv_row(const Row
     uint32_t o[2] = {0, 0};
 #pragma unroll
     for (int a = N - 2; a >= 0; a--) { o[a] = orow % (uint32_t)p.O[a]; orow /= (uint32_t)p.O[a]; }
-    int64_t tile = 0, row = 0, obase = 0;
+    int64_t tile = orow, row = 0, obase = orow;  // what is left of the row index is the batch index (0 without a batch)
 #pragma unroll
     for (int a = 0; a < N - 1; a++) {
         const uint32_t q = o[a] * (uint32_t)p.s[a];
@@ -964,7 +968,9 @@ struct ColTmaCfg {
     static constexpr int E = 32, Tc = 32, F = 1024, pitch = Tc * 8 + 8;
     static constexpr int group = 256, threads = 512;
     static constexpr int p_elems = F * 8, x_elems = E * pitch;                     // 8192, 8448 complex
-    static constexpr int smem = (p_elems + 2 * x_elems + F) * 8 + 64 + 128;         // + mbarriers + alignment slack
+    static constexpr int tw_pitch = 34;                                             // twiddle table rows of 32 + 2: 16-byte aligned, conflict-free 128-bit reads
+    static constexpr int tw_elems = Tc * tw_pitch;
+    static constexpr int smem = (p_elems + 2 * x_elems + tw_elems) * 8 + 64 + 128;  // + mbarriers + alignment slack
     static constexpr int box_rows = 256;
 };
 
@@ -980,6 +986,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t mb, uint32_t parity)
 }
 __device__ __forceinline__ pc lds_pc(uint32_t a) { pc r; asm volatile("ld.shared.b64 %0, [%1];" : "=l"(r.v) : "r"(a)); return r; }
 __device__ __forceinline__ void sts_pc(uint32_t a, pc v) { asm volatile("st.shared.b64 [%0], %1;" ::"r"(a), "l"(v.v) : "memory"); }
+__device__ __forceinline__ void lds_pc2(uint32_t a, pc &x, pc &y) { asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(x.v), "=l"(y.v) : "r"(a)); }
 
 // INNER > 0: the row pitch of the tile (complex elements) as a compile-time constant, so the kernel-spectrum loads address with
 // immediates (1032 = the 2048-sample last-axis tile of the BASELINE workload); 0: read it from the parameters.
@@ -996,11 +1003,11 @@ col_pass_tma(const __grid_constant__ ColParams p, const __grid_constant__ CUtens
     const int c = lt & 7, i = lt >> 3;                       // column of the block, thread index inside the column (< 32)
     const uint32_t sP = smem_addr(base);
     const uint32_t sX = sP + C::p_elems * 8 + g * (C::x_elems * 8);
-    pc *s_tw = reinterpret_cast<pc *>(base + (C::p_elems + 2 * C::x_elems) * 8);      // s_tw[k1 * 32 + i] = W_F^{i k1}
-    const uint32_t sT = sP + (C::p_elems + 2 * C::x_elems) * 8 + i * 8;               // this thread's column of the table
-    const uint32_t mb0 = sP + (C::p_elems + 2 * C::x_elems + F) * 8;                   // full[0], full[1]: P holds an item for group 0 / 1
+    pc *s_tw = reinterpret_cast<pc *>(base + (C::p_elems + 2 * C::x_elems) * 8);      // s_tw[i * 34 + k1] = W_F^{i k1}: a thread reads its row two entries at a time
+    const uint32_t sT = sP + (C::p_elems + 2 * C::x_elems) * 8 + i * (C::tw_pitch * 8);
+    const uint32_t mb0 = sP + (C::p_elems + 2 * C::x_elems + C::tw_elems) * 8;         // full[0], full[1]: P holds an item for group 0 / 1
     const uint32_t mbg = mb0 + 8 * g;
-    for (int idx = tid; idx < F; idx += C::threads) s_tw[idx] = ld_pc(p.tw + (idx >> 5) * (idx & 31));
+    for (int idx = tid; idx < F; idx += C::threads) s_tw[(idx >> 5) * C::tw_pitch + (idx & 31)] = ld_pc(p.tw + (idx >> 5) * (idx & 31));
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb0));
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb0 + 8));
@@ -1045,7 +1052,11 @@ col_pass_tma(const __grid_constant__ ColParams p, const __grid_constant__ CUtens
         if (lt == 0 && w + gridDim.x < p.nwork) issue_load(w + gridDim.x, g ^ 1);             // P is drained: the other group's next item
         if (p.mode != 1) {
 #pragma unroll
-            for (int k1 = 0; k1 < E; k1++) sts_pc(sX + (k1 * pitch + i * 8 + c) * 8, pk::cmul(v[k1], lds_pc(sT + k1 * Tc * 8)));
+            for (int k1 = 0; k1 < E; k1 += 2) {
+                pc w0, w1; lds_pc2(sT + k1 * 8, w0, w1);
+                sts_pc(sX + (k1 * pitch + i * 8 + c) * 8, pk::cmul(v[k1], w0));
+                sts_pc(sX + ((k1 + 1) * pitch + i * 8 + c) * 8, pk::cmul(v[k1 + 1], w1));
+            }
             bar_group(1 + g);
 #pragma unroll
             for (int ii = 0; ii < Tc; ii++) v[ii] = lds_pc(sX + (i * pitch + ii * 8 + c) * 8);
@@ -1063,7 +1074,11 @@ col_pass_tma(const __grid_constant__ ColParams p, const __grid_constant__ CUtens
             // square case: the rows this thread holds (i + 32 k2) are the rows the forward-structured flow starts from, so the
             // inverse is the forward flow with conjugated twiddles (mode INV: its first butterfly ran before the barrier above)
 #pragma unroll
-            for (int n1 = 0; n1 < E; n1++) sts_pc(sX + (n1 * pitch + i * 8 + c) * 8, pk::cmulc(v[n1], lds_pc(sT + n1 * Tc * 8)));
+            for (int n1 = 0; n1 < E; n1 += 2) {
+                pc w0, w1; lds_pc2(sT + n1 * 8, w0, w1);
+                sts_pc(sX + (n1 * pitch + i * 8 + c) * 8, pk::cmulc(v[n1], w0));
+                sts_pc(sX + ((n1 + 1) * pitch + i * 8 + c) * 8, pk::cmulc(v[n1 + 1], w1));
+            }
             bar_group(1 + g);
 #pragma unroll
             for (int ii = 0; ii < Tc; ii++) v[ii] = lds_pc(sX + (i * pitch + ii * 8 + c) * 8);
