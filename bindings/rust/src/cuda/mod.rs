@@ -26,8 +26,12 @@ use crate::conv_fft::{GetProcessor, Processor};
 use crate::dilation::{IntoKernelWithDilation, KernelWithDilation};
 use crate::{BorderType, ConvExt, ConvFFTExt, ConvMode, Error, PaddingMode};
 
-/// Host arrays at least this large are page-locked for the duration of a call (registering costs ~0.1 ms per MB and lifts
-/// host<->device traffic from 30-40 GB/s, staged through bounce buffers, to 70-80 GB/s).
+/// Host arrays at least this large take the library's pipelined path (H2D | kernels | D2H over axis-0 slabs).  An `Array` owns
+/// pageable `Vec` memory: the library then stages the slabs through its own pinned bounce buffers (30-40 GB/s of host<->device
+/// traffic; c5: 311 ms per call).  Page-locking the caller's allocation in place lifts that to 70-80 GB/s (c5: 101 ms) but costs
+/// ~0.1 ms per MB (c5: ~0.43 s per array), so it only pays for an allocation that serves several calls: the binding registers
+/// an allocation the SECOND time it sees it (same pointer and length) and keeps it registered until `unregister_all()` or thread
+/// exit; one-shot arrays never pay for registration.
 pub const AUTO_REGISTER_BYTES: usize = 96 << 20;
 
 /// Element types the device path takes; `DTYPE` is the `ndconv_dtype` code.
@@ -154,12 +158,54 @@ impl Pinned {
         let ptr = s.as_ptr() as *mut c_void;
         (unsafe { ffi::ndconv_host_register(ptr, std::mem::size_of_val(s)) } == ffi::OK).then_some(Self { ptr })
     }
-    /// page-lock `s` when it is large enough to pay for it and contiguous; a failed registration is not an error (the
-    /// library then stages the pageable array through its own pinned bounce buffers)
-    fn auto<T, S: Data<Elem = T>, D: Dimension>(a: &ArrayBase<S, D>) -> Option<Self> {
-        let s = a.as_slice_memory_order()?;
-        (std::mem::size_of_val(s) >= AUTO_REGISTER_BYTES).then(|| Self::new(s)).flatten()
+}
+
+/// Allocations seen by large host calls on this thread: (pointer, bytes) -> calls seen; registered from the second sighting on.
+#[derive(Default)]
+struct Registrations {
+    seen: Vec<(usize, usize, u32)>,
+    pinned: Vec<(usize, usize, Pinned)>,
+}
+thread_local! {
+    static REGISTRATIONS: std::cell::RefCell<Registrations> = Default::default();
+}
+
+/// Note a large contiguous host array; page-lock it when it has been seen before.  A failed registration is not an error (the
+/// library stages pageable arrays through its own pinned bounce buffers).  Freshly allocated outputs are never registered.
+fn note_host_array<T, S: Data<Elem = T>, D: Dimension>(a: &ArrayBase<S, D>) {
+    let Some(s) = a.as_slice_memory_order() else { return };
+    let (ptr, bytes) = (s.as_ptr() as usize, std::mem::size_of_val(s));
+    if bytes < AUTO_REGISTER_BYTES {
+        return;
     }
+    REGISTRATIONS.with(|r| {
+        let mut r = r.borrow_mut();
+        if r.pinned.iter().any(|(p, b, _)| *p == ptr && *b == bytes) {
+            return;
+        }
+        // an allocation that overlaps a registered one at another size was freed and reused: drop the stale registration
+        r.pinned.retain(|(p, b, _)| ptr + bytes <= *p || *p + *b <= ptr);
+        if let Some(e) = r.seen.iter_mut().find(|(p, b, _)| *p == ptr && *b == bytes) {
+            e.2 += 1;
+            if let Some(pin) = Pinned::new(s) {
+                r.pinned.push((ptr, bytes, pin));
+            }
+        } else {
+            if r.seen.len() >= 64 {
+                r.seen.remove(0);
+            }
+            r.seen.push((ptr, bytes, 1));
+        }
+    });
+}
+
+/// Release every page-lock this thread holds (call before freeing long-lived input arrays that were registered automatically).
+pub fn unregister_all() {
+    REGISTRATIONS.with(|r| {
+        let mut r = r.borrow_mut();
+        r.pinned.clear();
+        r.seen.clear();
+    });
 }
 impl Drop for Pinned {
     fn drop(&mut self) {
@@ -204,8 +250,7 @@ where
             Ok(o) => o,
             Err(st) => return check(st, self, &kwd, &conv_mode).map(|_| unreachable!()),
         };
-        let _pin_in = Pinned::auto(self);
-        let _pin_out = Pinned::auto(&out);
+        note_host_array(self);
         let st = DEVICES.with(|d| unsafe { ffi::ndconv_conv_direct(d.first().raw, &pr, out.as_mut_ptr() as *mut c_void) });
         check(st, self, &kwd, &conv_mode)?;
         Ok(out)
@@ -408,8 +453,7 @@ where
         Ok(o) => o,
         Err(st) => return check(st, data, &kwd, &conv_mode).map(|_| unreachable!()),
     };
-    let _pin_in = Pinned::auto(data);
-    let _pin_out = Pinned::auto(&out);
+    note_host_array(data);
     let outp = out.as_mut_ptr() as *mut c_void;
     let st = match call {
         FftCall::Fresh => unsafe { ffi::ndconv_conv_fft(std::ptr::null_mut(), &pr, outp) },
