@@ -234,8 +234,17 @@ def run_gpu(args, w, rank, world, local_rank):
     import torch.distributed as dist
     pkg = importlib.import_module("ndarray-conv_b200")
     lib = pkg.get_library()
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
+    # Which GPU a rank takes: with more GPUs visible than ranks, the ranks are spread evenly over the indices (N = 2 on an 8-GPU
+    # box -> GPUs 0 and 4) instead of packing 0 .. N-1.  The host<->device legs of the e2e measurement share PCIe uplinks / host
+    # memory ports in groups of neighbouring GPUs (profiles/r02_pcie_probe_8gpu.jsonl: two GPUs of one group 25.7 GB/s each way
+    # per rank in duplex, one GPU from each group 34.3; four: 12.8 vs 17.8), so spreading is worth 1.3-1.4x end to end at N = 2 / 4.
+    # Device-resident numbers do not depend on it.  --gpu-pick linear restores local_rank -> GPU local_rank.
+    ngpu = torch.cuda.device_count()
+    stride = ngpu // world if (args.gpu_pick == "spread" and world > 1 and ngpu >= 2 * world) else 1
+    gpu_index = local_rank * stride
+    torch.cuda.set_device(gpu_index)
+    dev = torch.device("cuda", gpu_index)
+    local_rank = gpu_index
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -361,6 +370,29 @@ def run_gpu(args, w, rank, world, local_rank):
     if world > 1:
         dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
     t_e2e = float(t_e.item())
+    # ---- the box's own floor for that leg: this step's bytes, H2D and D2H at the same time on two streams, no kernels, every rank
+    # at once (what the host memory system / PCIe fabric of THIS box sustains; the e2e call cannot beat it) ----
+    copy_floor = None
+    if not args.no_e2e:
+        s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        def copies():
+            with torch.cuda.stream(s_in):
+                x_dev.copy_(x_pin, non_blocking=True)
+            with torch.cuda.stream(s_out):
+                y_pin.copy_(y_dev, non_blocking=True)
+        best = float("inf")
+        for i in range(3):
+            barrier()
+            t0 = time.perf_counter()
+            copies()
+            torch.cuda.synchronize(dev)
+            barrier()
+            if i:
+                best = min(best, time.perf_counter() - t0)
+        t_c = torch.tensor([best], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t_c, op=dist.ReduceOp.MAX)
+        copy_floor = float(t_c.item())
     h2d = torch.tensor([x_pin.numel() * 4 + k_host.nbytes], dtype=torch.float64, device=dev)
     d2h = torch.tensor([y_pin.numel() * 4], dtype=torch.float64, device=dev)
     if world > 1:
@@ -382,11 +414,15 @@ def run_gpu(args, w, rank, world, local_rank):
             "metric": metric_name(), "value": value, "unit": "Gsamples/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": w["desc"], "out_samples_per_step": total_out, "parallelism": f"overlap-save slabs along axis 0 x{world}, no collective",
+                       "gpu_pick": f"{args.gpu_pick}: rank r -> GPU {stride} r of {ngpu} visible",
                        "l2": "inputs (>= 0.5 GB per rank) are larger than the 126 MB L2; no explicit flush"},
             "gpu_launches": int(launches),
             "clocks": clk,
             "e2e": {"value": total_out / t_e2e / 1e9, "unit": "Gsamples/s", "h2d_bytes_per_step": int(h2d.item()), "d2h_bytes_per_step": int(d2h.item()),
-                    "ms_per_step": t_e2e * 1e3, "api": "ndconv_conv_fft(NDCONV_MEM_HOST) on pinned host buffers"},
+                    "ms_per_step": t_e2e * 1e3, "api": "ndconv_conv_fft(NDCONV_MEM_HOST) on pinned host buffers",
+                    "copy_floor_ms": None if copy_floor is None else copy_floor * 1e3,
+                    "frac_of_copy_floor": None if copy_floor is None else copy_floor / t_e2e,
+                    "copy_floor_note": "the same bytes copied H2D and D2H at once by every rank with no kernels in between, measured in this run: the host<->device ceiling of this box for this step"},
             "e2e_pageable": e2e_pageable,
             "roofline": roof,
             "pipeline_compulsory": {"alg_bytes": compulsory, "achieved": compulsory / (ms_step * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
@@ -625,6 +661,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true", help="kernel experiments only: skip the host-buffer leg (the line then has no valid e2e)")
     ap.add_argument("--no-shapes", action="store_true", help="skip the secondary per-shape numbers (configs c1-c4)")
     ap.add_argument("--no-verify", action="store_true", help="N > 1: skip the comparison of the assembled N-rank output with rank 0's one-GPU answer")
+    ap.add_argument("--gpu-pick", default="spread", choices=["spread", "linear"], help="N ranks on a box with more GPUs: spread them over the GPU indices (default) or take GPUs 0 .. N-1")
     ap.add_argument("--ref-sample", action="store_true", help="reference arm: force the bounded row-slab sample instead of the full workload")
     ap.add_argument("--ref-budget-s", type=float, default=150.0, help="reference arm: wall-clock budget for its repetitions (at least one timed step is always run)")
     args = ap.parse_args()

@@ -216,7 +216,8 @@ int ndconv_fft_backward(ndconv_processor *p, int dtype, int ndim, const int64_t 
  * src/conv_fft/good_size.rs:6-42 -- any F >= P is valid and unobservable), the kernel family, the spectra workspace it
  * needs on the device and whether the call is cut along axis 0. */
 typedef struct ndconv_plan_info {
-    int path;                 /* 0 generic FFT kernels, 1 sm_100a fast path, 2 direct kernel (kernel longer than one FFT tile) */
+    int path;                 /* 0 generic FFT kernels, 1 sm_100a fast path, 2 direct kernel (kernel longer than one FFT tile and not splittable),
+                                 3 kernel longer than one FFT tile on an axis: cut into n_tiles[axis] segments of tile_valid[axis] taps, summed */
     int ndim;
     int tile_len[6];          /* F_a: transform length of one overlap-save tile */
     int tile_valid[6];        /* V_a = F_a - Kd_a + 1 alias-free positions per tile */

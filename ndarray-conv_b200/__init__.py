@@ -641,7 +641,7 @@ def plan_query(x_shape, dtype, kernel, conv_mode, padding_mode, memory=MEM_DEVIC
     info = _PlanInfo()
     lib.check(lib.c.ndconv_plan_query(ctypes.byref(pr), ctypes.byref(info)))
     nd = info.ndim
-    return {"path": ("generic", "fast", "direct")[info.path], "tile_len": list(info.tile_len[:nd]), "tile_valid": list(info.tile_valid[:nd]),
+    return {"path": ("generic", "fast", "direct", "split")[info.path], "tile_len": list(info.tile_len[:nd]), "tile_valid": list(info.tile_valid[:nd]),
             "n_tiles": list(info.n_tiles[:nd]), "workspace_bytes": int(info.workspace_bytes), "split_out_rows": int(info.split_out_rows),
             "pipelined": bool(info.pipelined)}
 

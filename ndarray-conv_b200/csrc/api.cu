@@ -712,7 +712,12 @@ int ndconv_plan_query(const ndconv_problem *problem, ndconv_plan_info *out)
     Geom g; std::vector<int32_t> maps[NDC_MAX_DIM];
     int st = check_problem(problem, NDCONV_PATH_FFT, &g, maps); if (st) return st;
     out->ndim = g.ndim;
-    if (kernel_exceeds_fft_tiles(problem)) { out->path = 2; return NDCONV_OK; }       // evaluated by the direct kernel
+    if (kernel_exceeds_fft_tiles(problem)) {                                            // longer than one FFT tile on some axis:
+        int ax = -1; int64_t seg = 0;
+        out->path = split_kernel_plan(problem, g, &ax, &seg) ? 3 : 2;                   // 3: cut into segments, each through the pipeline; 2: direct kernel
+        if (out->path == 3) { out->tile_valid[ax] = (int)seg; out->n_tiles[ax] = (int)((g.k[ax] + seg - 1) / seg); }
+        return NDCONV_OK;
+    }
     PlanEntry e;
     st = make_plan(g, &e.pl); if (st) return st;
     plan_axis0_split(problem, g, e.pl, &e);

@@ -646,4 +646,39 @@ template <class R> struct PermuteBody {
     }
 };
 
+
+// ---- Bluestein (chirp-z) for axes with a large prime factor: a length-n DFT as a length-M circular convolution, M >= 2n - 1 a power of two
+//   X[k] = w[k] * sum_j (x[j] w[j]) conj(w[k - j]),   w[j] = exp(-+ i pi j^2 / n)
+// mode 0: dst[o][j][i] = src[o][j][i] * w[j] for j < n, 0 for n <= j < M      ([outer][n][inner] -> [outer][M][inner])
+// mode 1: dst[o][m][i] *= bspec[m]                                           (spectrum of the chirp kernel, 1 / M folded in)
+// mode 2: dst[o][k][i] = src[o][k][i] * w[k] for k < n                        ([outer][M][inner] -> [outer][n][inner])
+template <class R> struct ChirpParams {
+    const cx<R> *src;
+    cx<R> *dst;
+    const cx<R> *w;        // chirp, n entries (already conjugated for the inverse direction)
+    const cx<R> *bspec;    // M entries
+    int64_t n, M, inner, outer;
+    int mode;
+};
+template <class R> struct ChirpBody {
+    static HD void run(const BlockCtx &c, const ChirpParams<R> &p)
+    {
+        const int64_t len = p.mode == 2 ? p.n : p.M, total = p.outer * len * p.inner;
+        for (int64_t e = c.bid * c.nt + c.tid; e < total; e += c.nb * c.nt) {
+            const int64_t i = e % p.inner, j = (e / p.inner) % len, o = e / (p.inner * len);
+            if (p.mode == 0) p.dst[e] = j < p.n ? cmul(p.src[(o * p.n + j) * p.inner + i], p.w[j]) : cx<R>{(R)0, (R)0};
+            else if (p.mode == 1) p.dst[e] = cmul(p.dst[e], p.bspec[j]);
+            else p.dst[e] = cmul(p.src[(o * p.M + j) * p.inner + i], p.w[j]);
+        }
+    }
+};
+
+// out[e] += add[e] over `n` real scalars (float or double): accumulation of the partial convolutions of a split kernel
+template <class R> struct AccumParams { R *out; const R *add; int64_t n; };
+template <class R> struct AccumBody {
+    static HD void run(const BlockCtx &c, const AccumParams<R> &p)
+    {
+        for (int64_t e = c.bid * c.nt + c.tid; e < p.n; e += c.nb * c.nt) p.out[e] = p.out[e] + p.add[e];
+    }
+};
 }  // namespace ndc

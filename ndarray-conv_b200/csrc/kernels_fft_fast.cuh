@@ -132,10 +132,14 @@ template <int N> __device__ __forceinline__ RowSrcInfo resolve_fwd_row(const Row
     return r;
 }
 
+// (Measured and rejected, round 2: ONE CTA of 16 warps per SM meeting at a barrier before every row, so that the warps of a scheduler
+// fetch the same instruction lines together -- `no_instructions` is 21 % of this kernel's stall samples, 11 % of row_inv's,
+// profiles/r02_ncu_full_c5s.md.  c5: row_fwd 1.94 -> 1.98 ms, row_inv 1.64 -> 1.69 ms, profiles/r02_variants_row_lockstep.log.)
 template <int T, int N>
 __global__ void __launch_bounds__(128, 4) row_fwd(const __grid_constant__ RowParams p)
 {
     pdl_launch_dependents();
+    constexpr int WPB = 4;
     constexpr int L = RowCfg<T>::L, M = RowCfg<T>::M, G = RowCfg<T>::G;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     pc *s_tw = reinterpret_cast<pc *>(smem_raw);          // s_tw[k1 * T + t] = W_L^{t k1}
@@ -152,7 +156,7 @@ __global__ void __launch_bounds__(128, 4) row_fwd(const __grid_constant__ RowPar
     const int src_lane = g * T + ((T - t) % T);
     const pc half = pk::mk(0.5f, 0.5f);
     const int64_t nwarp_items = (p.nwork + G - 1) / G;
-    for (int64_t wi = (int64_t)blockIdx.x * 4 + warp; wi < nwarp_items; wi += (int64_t)gridDim.x * 4) {
+    for (int64_t wi = (int64_t)blockIdx.x * WPB + warp; wi < nwarp_items; wi += (int64_t)gridDim.x * WPB) {
         const RowSrcInfo ri = resolve_fwd_row<N>(p, wi * G + g, L + kPad);
         if (__all_sync(0xffffffffu, !ri.active || ri.beyond)) {
             // rows beyond the padded extent of an outer axis: zero spectrum, no transform
@@ -281,6 +285,7 @@ template <int T, int N>
 __global__ void __launch_bounds__(128, 4) row_inv(const __grid_constant__ RowParams p)
 {
     pdl_launch_dependents();
+    constexpr int WPB = 4;
     constexpr int L = RowCfg<T>::L, M = RowCfg<T>::M, G = RowCfg<T>::G;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     pc *s_tw = reinterpret_cast<pc *>(smem_raw);          // TRANSPOSED for the inverse flow: s_tw[i * 32 + k1] = W_L^{i k1} (k1 is the lane-dependent index)
@@ -297,8 +302,8 @@ __global__ void __launch_bounds__(128, 4) row_inv(const __grid_constant__ RowPar
     constexpr int al = N - 1;
     const int src_lane = g * T + ((T - t) % T);
     const int64_t nwarp_items = (p.nwork + G - 1) / G;
-    const int64_t wstep = (int64_t)gridDim.x * 4;
-    int64_t wi = (int64_t)blockIdx.x * 4 + warp;
+    const int64_t wstep = (int64_t)gridDim.x * WPB;
+    int64_t wi = (int64_t)blockIdx.x * WPB + warp;
     if (wi >= nwarp_items) return;
     RowInvInfo ri = resolve_inv_row<N>(p, wi * G + g, L + kPad);
     auto stage = [&](const RowInvInfo &r) {

@@ -62,7 +62,9 @@ def test_tile_identities(pkg, q):
 def test_path_selection(pkg, q):
     assert q((300, 500), np.float64, z((5, 7), np.float64), pkg.ConvMode.Same, pkg.PaddingMode.Zeros)["path"] == "generic"       # no f64 fast path yet
     assert q((3, 4, 5, 6), np.float32, z((2, 2, 2, 2)), pkg.ConvMode.Same, pkg.PaddingMode.Zeros)["path"] == "generic"           # rank 4
-    assert q((100000,), np.float32, z((9001,)), pkg.ConvMode.Valid, pkg.PaddingMode.Zeros)["path"] == "direct"                   # kernel longer than one FFT tile
+    long1 = q((100000,), np.float32, z((9001,)), pkg.ConvMode.Valid, pkg.PaddingMode.Zeros)                                      # kernel longer than one FFT tile:
+    assert long1["path"] == "split" and long1["n_tiles"] == [3] and long1["tile_valid"] == [4096]                                # cut into segments of <= cap / 2 taps
+    assert q((100000,), np.float32, z((9001,)), pkg.ConvMode.Same, pkg.PaddingMode.Circular)["path"] == "direct"                 # a Circular border on the cut axis: direct kernel
     with pytest.raises(pkg.NdConvError) as e:
         q((3, 3), np.float32, z((5, 5)), pkg.ConvMode.Valid, pkg.PaddingMode.Zeros)
     assert e.value.status == pkg.ERR_MISMATCH_SHAPE

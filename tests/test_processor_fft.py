@@ -18,7 +18,9 @@ SHAPES = [(16,), (30,), (6, 10), (12, 40), (4, 6, 8), (5, 7, 12), (3, 4, 5, 6)]
 # outside the shared-memory envelope -> global-memory Stockham passes: odd real axes, prime factors above 7 (rustfft takes any
 # length: real.rs:40,62, complex.rs:56), axes longer than one shared-memory transform
 ANY_LENGTH_SHAPES = [(1,), (7,), (22,), (13,), (97,), (1, 1), (11, 13), (6, 15), (26, 34), (3, 5, 7), (2, 11, 9), (17, 4, 6), (3, 2, 5, 3),
-                     (1100, 6), (3, 1056, 4), (2, 9000), (8400,)]
+                     (1100, 6), (3, 1056, 4), (2, 9000), (8400,),
+                     # prime factors above 97: chirp-z (Bluestein) through power-of-two passes instead of an O(n r) generic pass
+                     (101,), (2, 1009), (211, 4), (3, 202, 5), (2018,)]
 
 
 @pytest.mark.parametrize("shape", SHAPES, ids=str)

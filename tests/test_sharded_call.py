@@ -73,6 +73,7 @@ def test_sharded_equals_single(pkg, cuda_lib, case, nproc):
     cm, pm = _modes(pkg, mode, padding)
     kern = pkg.with_dilation(k, dil) if dil > 1 else k
     ndev = cuda_lib.c.ndconv_device_count()
+    print(f"[sharded_call] visible GPUs: {ndev} -> {nproc} handles on {'distinct devices' if ndev >= nproc else ('devices ' + str([i % ndev for i in range(nproc)]))}")
     procs = [pkg.get_fft_processor(i % ndev, cuda_lib) for i in range(nproc)]
     got = pkg.conv_fft_sharded(x, kern, cm, pm, procs)
     assert all(p.launch_count > 0 for p in procs)           # every handle produced its rows
