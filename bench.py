@@ -519,6 +519,9 @@ def other_shapes(pkg, lib, proc, dev, stream):
         ("c2 x64 stacked: x=(64,200,5000) k=(1,11,31) dil (1,2,2) Same [Zeros,Reflect,Circular]", "fft", np.float32, (64, 200, 5000), (1, 11, 31), [1, 2, 2], pkg.ConvMode.Same,
          pkg.PaddingMode.Custom([B.Zeros, B.Reflect, B.Circular])),
         ("c3 x64 stacked: x=(64,10,100,200) k=(1,5,11,31) Same Zeros", "fft", np.float32, (64, 10, 100, 200), (1, 5, 11, 31), 1, pkg.ConvMode.Same, pkg.PaddingMode.Zeros),
+        # f64 (and rank >= 4) run on the generic kernels, not the sm_100a fast path: the same shape in both precisions, for the record
+        ("extra 2D f32 x=(8192,8192) k=(63,63) Full Reflect (fast path)", "fft", np.float32, (8192, 8192), (63, 63), 1, pkg.ConvMode.Full, pkg.PaddingMode.Reflect),
+        ("extra 2D f64 x=(8192,8192) k=(63,63) Full Reflect (generic kernels)", "fft", np.float64, (8192, 8192), (63, 63), 1, pkg.ConvMode.Full, pkg.PaddingMode.Reflect),
         # the direct kernel in the throughput regime (not a BASELINE config): 75 multiply-adds per output make it ALU / shared-memory bound
         ("extra 3D direct conv i32 x=(256,1024,1024) k=(3,5,5) Same Replicate", "direct", np.int32, (256, 1024, 1024), (3, 5, 5), 1, pkg.ConvMode.Same, pkg.PaddingMode.Replicate),
     ]
@@ -533,15 +536,15 @@ def other_shapes(pkg, lib, proc, dev, stream):
             kr = np.random.default_rng(2000 + ci)
             kh = (kr.random(ks, dtype=np.float32) + 1j * kr.random(ks, dtype=np.float32)).astype(np.complex64)
         else:
-            xh = rng.random(xs, dtype=np.float32)
-            kh = np.random.default_rng(2000 + ci).random(ks, dtype=np.float32)
+            xh = rng.random(xs, dtype=np.float32).astype(dt)
+            kh = np.random.default_rng(2000 + ci).random(ks, dtype=np.float32).astype(dt)
         xd = torch.from_numpy(xh.view(np.float32) if dt == np.complex64 else xh).to(dev)
         kw = pkg.with_dilation(kh, dil)
         entry = "ndconv_conv_fft" if path == "fft" else "ndconv_conv_direct"
         strides = [int(np.prod(xs[i + 1:])) for i in range(len(xs))]
         prep = pkg.PreparedConv(entry, proc, xs, strides, dt, kw, mode, pm)
         n_out = int(np.prod(prep.out_shape))
-        yd = torch.empty(n_out * (2 if dt == np.complex64 else 1), dtype=torch.int32 if dt == np.int32 else torch.float32, device=dev)
+        yd = torch.empty(n_out * (2 if dt == np.complex64 else 1), dtype=torch.int32 if dt == np.int32 else (torch.float64 if dt == np.float64 else torch.float32), device=dev)
         xp, yp = xd.data_ptr(), yd.data_ptr()
         call = lambda: prep(xp, yp)
         for _ in range(5):

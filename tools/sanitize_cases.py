@@ -41,5 +41,34 @@ for shp, dt in (((1100, 6), np.float32), ((5, 26, 9), np.float64), ((2, 9000), n
 proc2 = pkg.get_fft_processor(0)
 pkg.conv_fft_sharded(rng.random((3000, 4200), dtype=np.float32), k, pkg.ConvMode.Full, pkg.PaddingMode.Reflect, [proc, proc2])
 proc2.close()
+# round 2: TMA-fed 1024-row column pass (modes FWD / INV / FMI, row pitch 1032 and others), same-shape batch fold, i128 direct conv,
+# a kernel longer than one FFT tile (cut into segments), Bluestein axes, device-resident shards with ghost rows (two handles)
+pkg.conv_fft_with_processor(rng.random((1100, 2100), dtype=np.float32), k, pkg.ConvMode.Full, pkg.PaddingMode.Reflect, proc)
+pkg.conv_fft_with_processor(rng.random((3, 1000, 300), dtype=np.float32), rng.random((2, 3, 5), dtype=np.float32), pkg.ConvMode.Same, pkg.PaddingMode.Reflect, proc)
+pkg.conv_fft_with_processor(rng.random((1000, 20, 300), dtype=np.float32), rng.random((3, 3, 3), dtype=np.float32), pkg.ConvMode.Full, pkg.PaddingMode.Replicate, proc)
+pkg.conv_fft_with_processor(rng.random((5, 200, 700), dtype=np.float32), rng.random((1, 5, 7), dtype=np.float32), pkg.ConvMode.Same,
+                            pkg.PaddingMode.Custom([B.Zeros, B.Reflect, B.Circular]), proc)
+pkg.conv(pkg.int128_array(rng.integers(-9, 9, size=(6, 20, 24)).astype(object) * (1 << 70)), pkg.int128_array(rng.integers(-3, 3, size=(3, 3, 3)).astype(object)),
+         pkg.ConvMode.Same, pkg.PaddingMode.Replicate, processor=proc)
+pkg.conv_fft_with_processor(rng.random((2600, 40), dtype=np.float32), rng.random((1500, 3), dtype=np.float32), pkg.ConvMode.Same, pkg.PaddingMode.Replicate, proc)
+for shp, dt in (((2, 1009), np.float32), ((211, 4), np.complex64)):
+    xx = rng.random(shp).astype(dt)
+    s = proc.forward(xx); proc.backward(s)
+import torch
+procs = [pkg.get_fft_processor(0), pkg.get_fft_processor(0)]
+kk = rng.random((9, 5), dtype=np.float32)
+rows = [700, 800]
+pl = [pkg.shard_plan((1500, 1300), np.float32, kk, pkg.ConvMode.Full, pkg.PaddingMode.Reflect, rows, g) for g in range(2)]
+bufs, outs, shards = [], [], []
+for g in range(2):
+    hf, hb = pl[g]["halo_front"], pl[g]["halo_back"]
+    buf = torch.rand((hf + rows[g] + hb, 1300), dtype=torch.float32, device="cuda")
+    o = torch.empty((pl[g]["out_end"] - pl[g]["out_begin"], 1304), dtype=torch.float32, device="cuda")
+    bufs.append(buf); outs.append(o)
+    shards.append(dict(data=buf.data_ptr() + hf * 1300 * 4, rows=rows[g], halo_front=hf, halo_back=hb, out=o.data_ptr()))
+torch.cuda.synchronize()
+pkg.conv_fft_sharded_device(procs, (1500, 1300), np.float32, kk, pkg.ConvMode.Full, pkg.PaddingMode.Reflect, shards)
+for q in procs:
+    q.synchronize(); q.close()
 proc.close()
 print("SANITIZE_CASES_DONE")
