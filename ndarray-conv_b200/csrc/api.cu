@@ -620,7 +620,7 @@ int ndconv_processor_destroy(ndconv_processor *p)
 #endif
     for (auto &kv : p->tw_c) be_free(kv.second);
     for (auto &kv : p->tw_r) be_free(kv.second);
-    for (auto &k : p->kspecs) { k->buf.release(); k->pair.release(); }
+    for (auto &k : p->kspecs) { k->buf.release(); k->pair.release(); k->kres.release(); }
 #ifdef NDCONV_CUDA
     if (p->own_stream) cudaStreamDestroy(p->own_stream);
 #endif

@@ -830,6 +830,10 @@ struct ColParams {
     int64_t nwork;          // ntiles_total * outer * inner / 8
     int skip;               // modes 1 / 2: the first `skip` rows of the axis (= Kd - 1, the aliased head the crop discards) are not stored
     int store_rows;         // col_pass_tma: rows per store box (divides F - skip)
+    // col_pass_tma_kres (mode 2, outer == 1): the kernel spectrum regrouped per 8-column block in the order Tensor Memory takes it,
+    // and the bundle geometry of the work order (tiles of one block are taken `bundle` at a time; the last bundle has `bundle_last`)
+    const cf *kres;
+    int bundle, nbundles, bundle_last;
 };
 
 template <int E, int Tc> struct ColCfg {
@@ -1113,6 +1117,233 @@ col_pass_tma(const __grid_constant__ ColParams p, const __grid_constant__ CUtens
     if (lt == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
+// ---- column pass, F = 1024, mode FMI, kernel spectrum resident in Tensor Memory ----------------------------------------------------
+// In col_pass_tma every item re-reads its 64 KB of kernel spectrum from L2 (32 LDG.64 per thread with no registers left to issue them
+// early): measured 0.50 ms of the 2.5 ms pass on c5 (profiles/r02m_col_upper_bounds.log).  The spectrum of an 8-column block is the
+// same for every tile, so this variant changes the work order -- a CTA stays on one block for a CHUNK of `bundle` (>= 10) tiles -- and
+// keeps the block's spectrum in TENSOR MEMORY, which this FFT kernel has no other use for: each thread's 32 factors sit in its own
+// TMEM lane (32x32b shape: lane = thread of the warp quadrant, 64 columns per thread; the two warps of a group that share a quadrant
+// take columns [0, 64) / [64, 128) of a 128-column slot) and are read back with tcgen05.ld right where the multiply needs them:
+// 41 cycles of latency instead of an L2 round trip, no shared-memory or L1 wavefronts, no address arithmetic.
+//   * two slots (256 of the 512 columns): the current chunk's spectrum and the next chunk's, which arrives in eight 8 KB parts, one
+//     per item: a 1-D bulk copy (cp.async.bulk, mbarrier-tracked) into the group's scratch buffer at the start of the item, then at
+//     its end two LDS.128 + one tcgen05.st.x8 per thread.  `kres` holds the spectrum regrouped on the device once per kernel
+//     (KresBody) so that a part is contiguous: kres[block][part d][half h][thread lt][2] = factors k2 = 4 d + 2 h + {0, 1} of thread lt.
+//   * chunks of neighbouring CTAs are neighbouring blocks of the same tiles, so the DRAM page locality of the natural order is kept
+//     (a CTA that stays on a block while its neighbours move on halves the bandwidth: tools/exp/colcopy_probe.cu).
+//   * the two groups hand slots over through two counters in shared memory (`filled`: parts stored, `progress`: multiplies done);
+//     by construction the waits never spin (a chunk is at least two items longer than the eight that carry parts).
+// Work order: item j of CTA c (j = 0, 1, ...; group j & 1 takes it) is tile u * bundle + d of block kb, where chunk m = c + G * (j / len)
+// = u * blocks + kb.  Everything else -- butterflies, TMA box loads into P, TMA stores from the exchange buffer -- is col_pass_tma.
+struct ColKresCfg {
+    static constexpr int parts = 8, part_elems = 1024;                                    // 8 parts of 256 threads x 4 factors
+    static constexpr int scratch_off = (ColTmaCfg::p_elems + 2 * ColTmaCfg::x_elems + ColTmaCfg::tw_elems) * 8;
+    static constexpr int mbar_off = scratch_off + 2 * part_elems * 8;                     // full[0], full[1], scr[0], scr[1], pro ; filled[2], progress[2], tmem base
+    static constexpr int smem = mbar_off + 128 + 128;
+    static constexpr int min_bundle = 10;
+    static constexpr int tmem_cols = 256;
+};
+__device__ __forceinline__ void tm_ld32(uint32_t ta, uint32_t *r)
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]),
+                   "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]) : "r"(ta) : "memory");
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]),
+                   "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]) : "r"(ta + 16) : "memory");
+    // the wait names the registers so that no use of them can be scheduled above it
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]),
+                   "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]),
+                   "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31]) :: "memory");
+}
+__device__ __forceinline__ void tm_st8(uint32_t ta, uint4 a, uint4 b)
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"r"(ta), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t a) { uint4 r; asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(a)); return r; }
+__device__ __forceinline__ int lds_acquire(uint32_t a) { int r; asm volatile("ld.acquire.cta.shared.b32 %0, [%1];" : "=r"(r) : "r"(a) : "memory"); return r; }
+__device__ __forceinline__ void sts_release(uint32_t a, int v) { asm volatile("st.release.cta.shared.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ pc pc_of(uint32_t lo, uint32_t hi) { pc r; asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "r"(lo), "r"(hi)); return r; }
+
+template <int INNER>
+__global__ void __launch_bounds__(ColTmaCfg::threads, 1)
+col_pass_tma_kres(const __grid_constant__ ColParams p, const __grid_constant__ CUtensorMap tm_ld, const __grid_constant__ CUtensorMap tm_st)
+{
+    pdl_launch_dependents();
+    using C = ColTmaCfg;
+    using K = ColKresCfg;
+    constexpr int E = C::E, Tc = C::Tc, F = C::F, pitch = C::pitch;
+    extern __shared__ __align__(128) unsigned char smem_dyn[];
+    unsigned char *base = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 127) & ~(uintptr_t)127);
+    const int tid = threadIdx.x, g = tid >> 8, lt = tid & 255, wq = (tid >> 5) & 3;
+    const int c = lt & 7, i = lt >> 3;
+    const uint32_t sP = smem_addr(base);
+    const uint32_t sX = sP + C::p_elems * 8 + g * (C::x_elems * 8);
+    pc *s_tw = reinterpret_cast<pc *>(base + (C::p_elems + 2 * C::x_elems) * 8);
+    const uint32_t sT = sP + (C::p_elems + 2 * C::x_elems) * 8 + i * (C::tw_pitch * 8);
+    const uint32_t sS = sP + K::scratch_off + g * (K::part_elems * 8);       // this group's scratch part
+    const uint32_t mb0 = sP + K::mbar_off;                                    // full[0], full[1]
+    const uint32_t mbg = mb0 + 8 * g, mbs = mb0 + 16 + 8 * g, mbp = mb0 + 32; // scr[g], prologue
+    const uint32_t fl_filled = mb0 + 64, fl_progress = mb0 + 72, s_tbase = mb0 + 80;
+    for (int idx = tid; idx < F; idx += C::threads) s_tw[(idx >> 5) * C::tw_pitch + (idx & 31)] = ld_pc(p.tw + (idx >> 5) * (idx & 31));
+    if (tid == 0) {
+#pragma unroll
+        for (int b = 0; b < 5; b++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb0 + 8 * b));
+        asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(fl_filled), "r"(0) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if ((tid >> 5) == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_tbase), "r"((uint32_t)K::tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    uint32_t tbase; asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tbase) : "r"(s_tbase));
+    const uint32_t tq = tbase + ((uint32_t)(32 * wq) << 16) + (uint32_t)((lt >> 7) & 1) * 64;      // + slot * 128 + 2 * k2
+
+    const int64_t inner = INNER > 0 ? (int64_t)INNER : p.inner;
+    const uint32_t blocks = (uint32_t)(inner / 8), G = gridDim.x, cta = blockIdx.x;
+    const int D = p.bundle, Dl = p.bundle_last;
+    const uint32_t nq = (uint32_t)p.nbundles * blocks, nq_full = (uint32_t)(p.nbundles - 1) * blocks;     // chunks; chunks of full-length bundles
+    const int Mc = cta < nq ? (int)((nq - cta + G - 1) / G) : 0, Mfull = cta < nq_full ? (int)((nq_full - cta + G - 1) / G) : 0;
+    const int J = Mfull * D + (Mc - Mfull) * Dl;                               // items of this CTA
+    auto chunk_len = [&](int m) { return m < Mfull ? D : Dl; };
+    auto issue_load = [&](int m, int d, int gi) {
+        const uint32_t q = cta + (uint32_t)m * G, u = q / blocks, ib = q - u * blocks, t = u * (uint32_t)D + (uint32_t)d;
+        const uint32_t mb = mb0 + 8 * gi;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"((uint32_t)(C::p_elems * 8)) : "memory");
+#pragma unroll
+        for (int b = 0; b < F / C::box_rows; b++)
+            asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                         ::"r"(sP + b * C::box_rows * 64), "l"(reinterpret_cast<uint64_t>(&tm_ld)), "r"((int)(ib * 8)), "r"((int)(t * F + b * C::box_rows)), "r"(mb)
+                         : "memory");
+    };
+    pdl_wait();                                      // before the first access to the workspace (and to kres, which an earlier kernel of the stream wrote)
+    if (Mc > 0) {
+        // prologue: the first chunk's spectrum through P into slot 0 (all 512 threads: group g stores parts 4 g .. 4 g + 3)
+        if (tid == 0) {
+            const uint32_t kb = cta % blocks;
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbp), "r"((uint32_t)(K::parts * K::part_elems * 8)) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(sP), "l"(p.kres + (size_t)kb * (K::parts * K::part_elems)), "r"((uint32_t)(K::parts * K::part_elems * 8)), "r"(mbp) : "memory");
+        }
+        mbar_wait(mbp, 0);
+#pragma unroll
+        for (int dd = 0; dd < 4; dd++) {
+            const int d = 4 * g + dd;
+            const uint4 a = lds128(sP + ((d * 2 + 0) * 256 + lt) * 16), b = lds128(sP + ((d * 2 + 1) * 256 + lt) * 16);
+            tm_st8(tq + 8 * d, a, b);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();                                 // slot 0 complete; P read by everybody
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (tid == 0 && J > 0) issue_load(0, 0, 0);
+    uint32_t parity = 0, sparity = 0;
+    const int nst = (F - p.skip) / p.store_rows;
+    int m = 0, d = g, start = 0, m_checked = 0;      // chunk, position in it, CTA item index of the chunk's first item; the newest chunk whose slot this thread knows complete
+    while (m < Mc && d >= chunk_len(m)) { d -= chunk_len(m); start += chunk_len(m); m++; }
+    for (int j = g; j < J; j += 2) {
+        const uint32_t q = cta + (uint32_t)m * G, u = q / blocks, ib = q - u * blocks, t = u * (uint32_t)D + (uint32_t)d;
+        const bool carries_part = d < K::parts && m + 1 < Mc;      // group-uniform
+        pc v[32];
+        mbar_wait(mbg, parity);
+        parity ^= 1;
+#pragma unroll
+        for (int jj = 0; jj < 32; jj++) v[jj] = lds_pc(sP + ((i + 32 * jj) * 8 + c) * 8);
+        if (lt == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        pk::dft<false, E>(v);                        // consumes every loaded value before the barrier (see col_pass_tma)
+        bar_group(1 + g);
+        if (lt == 0) {
+            if (j + 1 < J) { int m1 = m, d1 = d + 1; if (d1 >= chunk_len(m)) { d1 = 0; m1++; } issue_load(m1, d1, g ^ 1); }
+            if (carries_part) {                      // part d of the next chunk's spectrum -> this group's scratch
+                const uint32_t kb = (q + G) % blocks;
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbs), "r"((uint32_t)(K::part_elems * 8)) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(sS), "l"(p.kres + ((size_t)kb * K::parts + d) * K::part_elems), "r"((uint32_t)(K::part_elems * 8)), "r"(mbs) : "memory");
+            }
+            sts_release(fl_filled + 4 * g, j);       // every earlier item of this group has stored its part (all threads passed the barrier above)
+        }
+#pragma unroll
+        for (int k1 = 0; k1 < E; k1 += 2) {
+            pc w0, w1; lds_pc2(sT + k1 * 8, w0, w1);
+            sts_pc(sX + (k1 * pitch + i * 8 + c) * 8, pk::cmul(v[k1], w0));
+            sts_pc(sX + ((k1 + 1) * pitch + i * 8 + c) * 8, pk::cmul(v[k1 + 1], w1));
+        }
+        bar_group(1 + g);
+#pragma unroll
+        for (int ii = 0; ii < Tc; ii++) v[ii] = lds_pc(sX + (i * pitch + ii * 8 + c) * 8);
+        pk::dft<false, Tc>(v);                       // v[k2] = row i + 32 k2
+        if (m > m_checked) {
+            // first item of this group in chunk m: the other group's parts of it are stored once it has published an item index
+            // above the chunk's last part-carrying item (start - len(m - 1) + 7)
+            const int need = start - chunk_len(m - 1) + K::parts;
+            while (lds_acquire(fl_filled + 4 * (g ^ 1)) < need) { }
+            m_checked = m;
+        }
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        {
+            const uint32_t ts = tq + (uint32_t)(m & 1) * 128;
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                uint32_t r[32];
+                tm_ld32(ts + 32 * h, r);
+#pragma unroll
+                for (int e = 0; e < 16; e++) v[16 * h + e] = pk::cmul(v[16 * h + e], pc_of(r[2 * e], r[2 * e + 1]));
+            }
+        }
+        pk::dft<true, E>(v);
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        bar_group(1 + g);                            // every thread has finished reading the exchange buffer (and this item's slot)
+        if (lt == 0) sts_release(fl_progress + 4 * g, j + 1);
+#pragma unroll
+        for (int n1 = 0; n1 < E; n1 += 2) {
+            pc w0, w1; lds_pc2(sT + n1 * 8, w0, w1);
+            sts_pc(sX + (n1 * pitch + i * 8 + c) * 8, pk::cmulc(v[n1], w0));
+            sts_pc(sX + ((n1 + 1) * pitch + i * 8 + c) * 8, pk::cmulc(v[n1 + 1], w1));
+        }
+        bar_group(1 + g);
+#pragma unroll
+        for (int ii = 0; ii < Tc; ii++) v[ii] = lds_pc(sX + (i * pitch + ii * 8 + c) * 8);
+        pk::dft<true, E>(v);                         // v[jj] = row i + 32 jj
+        bar_group(1 + g);                            // exchange reads done: the buffer becomes the dense [row][8] store staging
+#pragma unroll
+        for (int jj = 0; jj < 32; jj++) sts_pc(sX + ((i + 32 * jj) * 8 + c) * 8, v[jj]);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        bar_group(1 + g);
+        if (lt == 0) {
+            for (int b = 0; b < nst; b++) {
+                const int r = p.skip + b * p.store_rows;
+                asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+                             ::"l"(reinterpret_cast<uint64_t>(&tm_st)), "r"((int)(ib * 8)), "r"((int)(t * F + r)), "r"(sX + r * 64) : "memory");
+            }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        if (carries_part) {
+            // scratch -> the other slot, which chunk m - 1 was read from: the other group must be past the multiply of its last item there
+            mbar_wait(mbs, sparity);
+            sparity ^= 1;
+            const uint4 a = lds128(sS + lt * 16), b = lds128(sS + (256 + lt) * 16);
+            if (m > 0) while (lds_acquire(fl_progress + 4 * (g ^ 1)) < start - 1) { }
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            tm_st8(tq + (uint32_t)((m + 1) & 1) * 128 + 8 * d, a, b);
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        }
+        d += 2;
+        while (m < Mc && d >= chunk_len(m)) { d -= chunk_len(m); start += chunk_len(m); m++; }
+    }
+    if (lt == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if ((tid >> 5) == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tbase), "r"((uint32_t)K::tmem_cols) : "memory");
+}
+
 }  // namespace fast
 
 // kernel spectrum [rows][Hp] in natural bin order (bins 0..L, generic path) -> the fast path's row layout (pitch L + 8):
@@ -1143,6 +1374,25 @@ struct KfastBody {
                 val = p.kspec[q * p.Hp + bin];
             }
             p.kfast[e] = val;
+        }
+    }
+};
+// fast-path kernel spectrum of a 1024-row axis-0 tile [1024][inner] -> the order col_pass_tma_kres streams into Tensor Memory:
+// kres[block][part d < 8][half h < 2][thread lt < 256][e < 2] = kfast[(i + 32 k2) * inner + 8 block + c], lt = 8 i + c, k2 = 4 d + 2 h + e
+struct KresParams {
+    const cx<float> *kfast;
+    cx<float> *kres;
+    int64_t inner;
+};
+struct KresBody {
+    static HD void run(const BlockCtx &c, const KresParams &p)
+    {
+        const int64_t total = 1024 * p.inner;
+        for (int64_t e = c.bid * c.nt + c.tid; e < total; e += c.nb * c.nt) {
+            const int64_t blk = e >> 13;
+            const int r = (int)(e & 8191), d = r >> 10, h = (r >> 9) & 1, lt = (r >> 1) & 255, ee = r & 1;
+            const int i = lt >> 3, cc = lt & 7, k2 = 4 * d + 2 * h + ee;
+            p.kres[e] = p.kfast[(int64_t)(i + 32 * k2) * p.inner + blk * 8 + cc];
         }
     }
 };
