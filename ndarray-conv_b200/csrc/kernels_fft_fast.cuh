@@ -25,6 +25,7 @@
 
 #ifdef NDCONV_CUDA
 #include <cuda.h>          // CUtensorMap (col_pass_tma)
+#include <type_traits>
 namespace ndc {
 namespace fast {
 
@@ -132,6 +133,32 @@ template <int N> __device__ __forceinline__ RowSrcInfo resolve_fwd_row(const Row
     return r;
 }
 
+// two neighbouring samples (padded columns cl, cl + 1 of the last axis) of a row that is not plain array data there: constant
+// borders, index-mapped borders, cells no padding pass writes (0), columns beyond the padded extent (0)
+template <int N> __device__ __noinline__ pc border_pair(const RowParams &p, int64_t base, int flags, float cval, int64_t cl0)
+{
+    constexpr int al = N - 1;
+    const bool active = flags & 1, beyond = flags & 2, zero = flags & 4, has_const = flags & 8;
+    const bool plain = active && !beyond && !zero && !has_const;
+    float q[2];
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const int64_t cl = cl0 + h;
+        float val = 0.f;
+        const int64_t cc = cl - p.pf[al];
+        if (plain && cc >= 0 && cc < p.n[al]) val = __ldg(p.x + base + cc * p.xstr[al]);      // in-array sample: no map lookup
+        else if (active && !beyond && cl < p.P[al]) {
+            const int32_t m = p.map[al][cl];
+            if (m == NDC_MAP_CONST_FRONT) val = p.cfront[al];
+            else if (m == NDC_MAP_CONST_BACK) val = p.cback[al];
+            else if (has_const) val = cval;
+            else if (m != NDC_MAP_INIT && !zero) val = __ldg(p.x + base + (int64_t)m * p.xstr[al]);
+        }
+        q[h] = val;
+    }
+    return pk::mk(q[0], q[1]);
+}
+
 // (Measured and rejected, round 2: ONE CTA of 16 warps per SM meeting at a barrier before every row, so that the warps of a scheduler
 // fetch the same instruction lines together -- `no_instructions` is 21 % of this kernel's stall samples, 11 % of row_inv's,
 // profiles/r02_ncu_full_c5s.md.  c5: row_fwd 1.94 -> 1.98 ms, row_inv 1.64 -> 1.69 ms, profiles/r02_variants_row_lockstep.log.)
@@ -156,8 +183,24 @@ __global__ void __launch_bounds__(128, 4) row_fwd(const __grid_constant__ RowPar
     const int src_lane = g * T + ((T - t) % T);
     const pc half = pk::mk(0.5f, 0.5f);
     const int64_t nwarp_items = (p.nwork + G - 1) / G;
-    for (int64_t wi = (int64_t)blockIdx.x * WPB + warp; wi < nwarp_items; wi += (int64_t)gridDim.x * WPB) {
-        const RowSrcInfo ri = resolve_fwd_row<N>(p, wi * G + g, L + kPad);
+    // The row AFTER this one is resolved (tile / row decode, outer-axis border maps: a chain of divisions and a dependent global load)
+    // and its samples are requested into L2 (prefetch.global.L2: no registers) before this row's transform starts, so neither the
+    // map lookup nor the DRAM latency of the samples sits in front of the next row's loads.
+    const int64_t wstep = (int64_t)gridDim.x * WPB;
+    int64_t wi = (int64_t)blockIdx.x * WPB + warp;
+    RowSrcInfo nxt = resolve_fwd_row<N>(p, wi * G + g, L + kPad);
+    for (; wi < nwarp_items; wi += wstep) {
+        const RowSrcInfo ri = nxt;
+        if (wi + wstep < nwarp_items) {
+            nxt = resolve_fwd_row<N>(p, (wi + wstep) * G + g, L + kPad);
+            if (nxt.active && !nxt.beyond && !nxt.zero && !nxt.has_const && p.xstr[al] == 1) {
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const int64_t cc = nxt.cl0 - p.pf[al] + 32 * (t + T * h);          // one 128-byte line per lane and half
+                    if (cc >= 0 && cc < p.n[al]) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.x + nxt.base + cc));
+                }
+            }
+        }
         if (__all_sync(0xffffffffu, !ri.active || ri.beyond)) {
             // rows beyond the padded extent of an outer axis: zero spectrum, no transform
             if (ri.active) {
@@ -180,27 +223,22 @@ __global__ void __launch_bounds__(128, 4) row_fwd(const __grid_constant__ RowPar
                 for (int j = 0; j < 32; j++) { const int e = 2 * (t + T * j); v[j] = pk::mk(__ldg(src + e), __ldg(src + e + 1)); }
             }
         } else {
-            const bool beyond = ri.beyond;
-            const bool plain = ri.active && !beyond && !ri.zero && !ri.has_const;
+            // a tile at the edge of the last axis (or a row with a constant / zero outer border): sample pairs that lie inside the array
+            // are still fetched 8 bytes at a time; only the pairs that touch the border go through the index map, in a function of
+            // its own -- unrolled inline 32 times it was 3 400 instructions that every edge-tile row (2 of c5's 17 tile columns)
+            // walked through at 2.7 x the cost of an interior row
+            const bool plain = ri.active && !ri.beyond && !ri.zero && !ri.has_const && p.xstr[al] == 1;
+            const float *rowp = p.x + ri.base - p.pf[al];                 // padded column cl of this row is rowp[cl] where it is an array sample
+            const int64_t lo = p.pf[al], hi = p.pf[al] + p.n[al];
+            const int flags = (ri.active ? 1 : 0) | (ri.beyond ? 2 : 0) | (ri.zero ? 4 : 0) | (ri.has_const ? 8 : 0);
 #pragma unroll
             for (int j = 0; j < 32; j++) {
-                float q[2];
-#pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    const int64_t cl = ri.cl0 + 2 * (t + T * j) + h;
-                    float val = 0.f;
-                    const int64_t cc = cl - p.pf[al];
-                    if (plain && cc >= 0 && cc < p.n[al]) val = __ldg(p.x + ri.base + cc * p.xstr[al]);      // in-array sample: no map lookup
-                    else if (ri.active && !beyond && cl < p.P[al]) {
-                        const int32_t m = p.map[al][cl];
-                        if (m == NDC_MAP_CONST_FRONT) val = p.cfront[al];
-                        else if (m == NDC_MAP_CONST_BACK) val = p.cback[al];
-                        else if (ri.has_const) val = ri.cval;
-                        else if (m != NDC_MAP_INIT && !ri.zero) val = __ldg(p.x + ri.base + (int64_t)m * p.xstr[al]);
-                    }
-                    q[h] = val;
-                }
-                v[j] = pk::mk(q[0], q[1]);
+                const int64_t cl = ri.cl0 + 2 * (t + T * j);
+                if (plain && cl >= lo && cl + 1 < hi) {
+                    const float *s = rowp + cl;
+                    if ((reinterpret_cast<uintptr_t>(s) & 7) == 0) v[j].v = __ldg(reinterpret_cast<const unsigned long long *>(s));
+                    else v[j] = pk::mk(__ldg(s), __ldg(s + 1));
+                } else v[j] = border_pair<N>(p, ri.base, flags, ri.cval, cl);
             }
         }
         pk::dft<false, 32>(v);                                           // over j -> k1
@@ -1141,7 +1179,8 @@ struct ColKresCfg {
     static constexpr int mbar_off = scratch_off + 2 * part_elems * 8;                     // full[0], full[1], scr[0], scr[1], pro ; filled[2], progress[2], tmem base
     static constexpr int smem = mbar_off + 128 + 128;
     static constexpr int min_bundle = 10;
-    static constexpr int tmem_cols = 256;
+    static constexpr int tmem_cols = 512;            // two spectrum slots (2 x 128 columns) + the twiddle slot (128 columns), rounded up to a power of two
+    static constexpr int tw_col = 256;
 };
 __device__ __forceinline__ void tm_ld32(uint32_t ta, uint32_t *r)
 {
@@ -1157,6 +1196,24 @@ __device__ __forceinline__ void tm_ld32(uint32_t ta, uint32_t *r)
                    "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]),
                    "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31]) :: "memory");
 }
+__device__ __forceinline__ void tm_ld16_issue(uint32_t ta, uint32_t *r)
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]),
+                   "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]) : "r"(ta) : "memory");
+}
+__device__ __forceinline__ void tm_wait16(uint32_t *r)
+{
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]),
+                   "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]) :: "memory");
+}
+__device__ __forceinline__ void tm_st16(uint32_t ta, const uint32_t *r)
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+                 ::"r"(ta), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]),
+                 "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+}
 __device__ __forceinline__ void tm_st8(uint32_t ta, uint4 a, uint4 b)
 {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
@@ -1167,7 +1224,7 @@ __device__ __forceinline__ int lds_acquire(uint32_t a) { int r; asm volatile("ld
 __device__ __forceinline__ void sts_release(uint32_t a, int v) { asm volatile("st.release.cta.shared.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ pc pc_of(uint32_t lo, uint32_t hi) { pc r; asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "r"(lo), "r"(hi)); return r; }
 
-template <int INNER>
+template <int INNER, bool TWT = true>
 __global__ void __launch_bounds__(ColTmaCfg::threads, 1)
 col_pass_tma_kres(const __grid_constant__ ColParams p, const __grid_constant__ CUtensorMap tm_ld, const __grid_constant__ CUtensorMap tm_st)
 {
@@ -1204,6 +1261,43 @@ col_pass_tma_kres(const __grid_constant__ ColParams p, const __grid_constant__ C
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     uint32_t tbase; asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tbase) : "r"(s_tbase));
     const uint32_t tq = tbase + ((uint32_t)(32 * wq) << 16) + (uint32_t)((lt >> 7) & 1) * 64;      // + slot * 128 + 2 * k2
+    if constexpr (TWT) {
+        // the thread's row of the twiddle table (W_F^{i k1}, k1 < 32) goes into Tensor Memory as well: 2 x 16 LDS.128 per item less
+        // on the shared-memory pipe (group g stores k1 in [16 g, 16 g + 16); both groups read the same cells)
+        uint32_t r[32];
+#pragma unroll
+        for (int e = 0; e < 16; e++) { const pc w = s_tw[i * C::tw_pitch + 16 * g + e]; r[2 * e] = (uint32_t)(w.v & 0xffffffffu); r[2 * e + 1] = (uint32_t)(w.v >> 32); }
+        tm_st16(tq + K::tw_col + 32 * g, r);
+        tm_st16(tq + K::tw_col + 32 * g + 16, r + 16);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    // v[k1] * W^{i k1} (CONJ: its conjugate) -> exchange buffer row k1
+    auto twiddle_exchange = [&](pc *v, auto conj_tag) {
+        constexpr bool CONJ = decltype(conj_tag)::value;
+        if constexpr (TWT) {
+            uint32_t r[2][16];
+            tm_ld16_issue(tq + K::tw_col, r[0]);
+            tm_wait16(r[0]);
+#pragma unroll
+            for (int ch = 0; ch < 4; ch++) {
+                if (ch < 3) tm_ld16_issue(tq + K::tw_col + 16 * (ch + 1), r[(ch + 1) & 1]);
+#pragma unroll
+                for (int e = 0; e < 8; e++) {
+                    const int k1 = 8 * ch + e;
+                    const pc w = pc_of(r[ch & 1][2 * e], r[ch & 1][2 * e + 1]);
+                    sts_pc(sX + (k1 * pitch + i * 8 + c) * 8, CONJ ? pk::cmulc(v[k1], w) : pk::cmul(v[k1], w));
+                }
+                if (ch < 3) tm_wait16(r[(ch + 1) & 1]);
+            }
+        } else {
+#pragma unroll
+            for (int k1 = 0; k1 < E; k1 += 2) {
+                pc w0, w1; lds_pc2(sT + k1 * 8, w0, w1);
+                sts_pc(sX + (k1 * pitch + i * 8 + c) * 8, CONJ ? pk::cmulc(v[k1], w0) : pk::cmul(v[k1], w0));
+                sts_pc(sX + ((k1 + 1) * pitch + i * 8 + c) * 8, CONJ ? pk::cmulc(v[k1 + 1], w1) : pk::cmul(v[k1 + 1], w1));
+            }
+        }
+    };
 
     const int64_t inner = INNER > 0 ? (int64_t)INNER : p.inner;
     const uint32_t blocks = (uint32_t)(inner / 8), G = gridDim.x, cta = blockIdx.x;
@@ -1269,12 +1363,7 @@ col_pass_tma_kres(const __grid_constant__ ColParams p, const __grid_constant__ C
             }
             sts_release(fl_filled + 4 * g, j);       // every earlier item of this group has stored its part (all threads passed the barrier above)
         }
-#pragma unroll
-        for (int k1 = 0; k1 < E; k1 += 2) {
-            pc w0, w1; lds_pc2(sT + k1 * 8, w0, w1);
-            sts_pc(sX + (k1 * pitch + i * 8 + c) * 8, pk::cmul(v[k1], w0));
-            sts_pc(sX + ((k1 + 1) * pitch + i * 8 + c) * 8, pk::cmul(v[k1 + 1], w1));
-        }
+        twiddle_exchange(v, std::false_type{});
         bar_group(1 + g);
 #pragma unroll
         for (int ii = 0; ii < Tc; ii++) v[ii] = lds_pc(sX + (i * pitch + ii * 8 + c) * 8);
@@ -1301,12 +1390,7 @@ col_pass_tma_kres(const __grid_constant__ ColParams p, const __grid_constant__ C
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         bar_group(1 + g);                            // every thread has finished reading the exchange buffer (and this item's slot)
         if (lt == 0) sts_release(fl_progress + 4 * g, j + 1);
-#pragma unroll
-        for (int n1 = 0; n1 < E; n1 += 2) {
-            pc w0, w1; lds_pc2(sT + n1 * 8, w0, w1);
-            sts_pc(sX + (n1 * pitch + i * 8 + c) * 8, pk::cmulc(v[n1], w0));
-            sts_pc(sX + ((n1 + 1) * pitch + i * 8 + c) * 8, pk::cmulc(v[n1 + 1], w1));
-        }
+        twiddle_exchange(v, std::true_type{});
         bar_group(1 + g);
 #pragma unroll
         for (int ii = 0; ii < Tc; ii++) v[ii] = lds_pc(sX + (i * pitch + ii * 8 + c) * 8);
