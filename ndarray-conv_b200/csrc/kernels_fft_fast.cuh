@@ -81,6 +81,7 @@ struct RowParams {
     // same-shape batch (a leading axis of kernel extent 1 folded away by the host): problem b reads x + b * xstr_batch, its tiles follow
     // those of problem b - 1 in the workspace and its output rows follow in `out`; the batch index is the outermost tile coordinate
     int64_t xstr_batch;
+    int pf_mode;                               // row_fwd, experiments: where the next row's samples are requested into L2 (0 never, 1 before this row's loads, 2 after its exchange)
 };
 
 // ---- row forward ---------------------------------------------------------------------------------------------------------
@@ -189,17 +190,20 @@ __global__ void __launch_bounds__(128, 4) row_fwd(const __grid_constant__ RowPar
     const int64_t wstep = (int64_t)gridDim.x * WPB;
     int64_t wi = (int64_t)blockIdx.x * WPB + warp;
     RowSrcInfo nxt = resolve_fwd_row<N>(p, wi * G + g, L + kPad);
+    auto prefetch_next = [&]() {
+        if (nxt.active && !nxt.beyond && !nxt.zero && !nxt.has_const && p.xstr[al] == 1) {
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int64_t cc = nxt.cl0 - p.pf[al] + 32 * (t + T * h);          // one 128-byte line per lane and half
+                if (cc >= 0 && cc < p.n[al]) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.x + nxt.base + cc));
+            }
+        }
+    };
     for (; wi < nwarp_items; wi += wstep) {
         const RowSrcInfo ri = nxt;
         if (wi + wstep < nwarp_items) {
             nxt = resolve_fwd_row<N>(p, (wi + wstep) * G + g, L + kPad);
-            if (nxt.active && !nxt.beyond && !nxt.zero && !nxt.has_const && p.xstr[al] == 1) {
-#pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    const int64_t cc = nxt.cl0 - p.pf[al] + 32 * (t + T * h);          // one 128-byte line per lane and half
-                    if (cc >= 0 && cc < p.n[al]) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.x + nxt.base + cc));
-                }
-            }
+            if (p.pf_mode == 1) prefetch_next();
         }
         if (__all_sync(0xffffffffu, !ri.active || ri.beyond)) {
             // rows beyond the padded extent of an outer axis: zero spectrum, no transform
@@ -250,6 +254,7 @@ __global__ void __launch_bounds__(128, 4) row_fwd(const __grid_constant__ RowPar
 #pragma unroll
             for (int i = 0; i < T; i++) v[m * T + i] = sb[(t + T * m) * (T + 1) + i];
         __syncwarp();
+        if (p.pf_mode == 2 && wi + wstep < nwarp_items) prefetch_next();
 #pragma unroll
         for (int m = 0; m < M; m++) pk::dft<false, T>(v + m * T);         // v[m*T + k2] = Z[k], k = t + T m + 32 k2
         // partner Z[L-k] and R2C post-processing; primaries are k2 < T/2 (k < L/2):
