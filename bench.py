@@ -519,9 +519,9 @@ def other_shapes(pkg, lib, proc, dev, stream):
         ("c2 x64 stacked: x=(64,200,5000) k=(1,11,31) dil (1,2,2) Same [Zeros,Reflect,Circular]", "fft", np.float32, (64, 200, 5000), (1, 11, 31), [1, 2, 2], pkg.ConvMode.Same,
          pkg.PaddingMode.Custom([B.Zeros, B.Reflect, B.Circular])),
         ("c3 x64 stacked: x=(64,10,100,200) k=(1,5,11,31) Same Zeros", "fft", np.float32, (64, 10, 100, 200), (1, 5, 11, 31), 1, pkg.ConvMode.Same, pkg.PaddingMode.Zeros),
-        # f64 (and rank >= 4) run on the generic kernels, not the sm_100a fast path: the same shape in both precisions, for the record
+        # the same shape in both precisions: f32 fast path (32 values per thread, packed FP32) and f64 fast path (16 values per thread; tiles of 512 x 256)
         ("extra 2D f32 x=(8192,8192) k=(63,63) Full Reflect (fast path)", "fft", np.float32, (8192, 8192), (63, 63), 1, pkg.ConvMode.Full, pkg.PaddingMode.Reflect),
-        ("extra 2D f64 x=(8192,8192) k=(63,63) Full Reflect (generic kernels)", "fft", np.float64, (8192, 8192), (63, 63), 1, pkg.ConvMode.Full, pkg.PaddingMode.Reflect),
+        ("extra 2D f64 x=(8192,8192) k=(63,63) Full Reflect (f64 fast path)", "fft", np.float64, (8192, 8192), (63, 63), 1, pkg.ConvMode.Full, pkg.PaddingMode.Reflect),
         # the direct kernel in the throughput regime (not a BASELINE config): 75 multiply-adds per output make it ALU / shared-memory bound
         ("extra 3D direct conv i32 x=(256,1024,1024) k=(3,5,5) Same Replicate", "direct", np.int32, (256, 1024, 1024), (3, 5, 5), 1, pkg.ConvMode.Same, pkg.PaddingMode.Replicate),
     ]

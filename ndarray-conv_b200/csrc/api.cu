@@ -20,6 +20,7 @@
 #include "kernels_direct.h"
 #include "kernels_fft.h"
 #include "kernels_fft_fast.cuh"
+#include "kernels_fft_fast_f64.cuh"
 #include "kernels_direct_tile.cuh"
 
 #ifdef NDCONV_CUDA
@@ -60,17 +61,26 @@ struct FftPlan {
     int64_t rows_per_tile = 1, tile_elems = 0, ntiles_total = 1;
 };
 
-// sm_100a fast path (kernels_fft_fast.cuh): real f32, rank 2 or 3, power-of-two overlap-save tiles
+// sm_100a fast path: real f32 / Complex<f32> of rank 1-3 (kernels_fft_fast.cuh), real f64 of rank 2-3 (kernels_fft_fast_f64.cuh);
+// power-of-two overlap-save tiles from the menus below
+static const int kMenuLast[4] = {256, 512, 1024, 2048}, kMenuLastCx[4] = {128, 256, 512, 1024}, kMenuCol[7] = {16, 32, 64, 128, 256, 512, 1024};
+static const int kMenuLastD[3] = {128, 256, 512}, kMenuColD[5] = {16, 32, 64, 128, 256};      // f64: sixteen values per thread
+static void fast_menus(int dtype, const int **last, int *nlast, const int **col, int *ncol)
+{
+    if (dtype == NDCONV_F64) { *last = kMenuLastD; *nlast = 3; *col = kMenuColD; *ncol = 5; }
+    else { *last = dtype == NDCONV_C32 ? kMenuLastCx : kMenuLast; *nlast = 4; *col = kMenuCol; *ncol = 7; }
+}
 static bool fast_eligible(const Geom &g)
 {
 #ifdef NDCONV_CUDA
-    static const bool disabled = getenv("NDCONV_DISABLE_OPT") != nullptr;
-    const bool cx32 = g.dtype == NDCONV_C32;
-    if (disabled || (g.dtype != NDCONV_F32 && !cx32) || g.ndim < 1 || g.ndim > 3) return false;
+    static const bool disabled = getenv("NDCONV_DISABLE_OPT") != nullptr, disabled64 = getenv("NDCONV_DISABLE_OPT64") != nullptr;
+    const bool cx32 = g.dtype == NDCONV_C32, f64 = g.dtype == NDCONV_F64;
+    if (disabled || (g.dtype != NDCONV_F32 && !cx32 && !f64) || g.ndim < 1 || g.ndim > 3) return false;
+    if (f64 && (disabled64 || g.ndim < 2)) return false;
     const int al = g.ndim - 1;
-    if (g.P[al] < (cx32 ? 64 : 128) || g.Kd[al] > (cx32 ? 512 : 1024)) return false;
+    if (g.P[al] < (cx32 ? 64 : 128) || g.Kd[al] > (cx32 ? 512 : (f64 ? 256 : 1024))) return false;
     int64_t tot = 1;
-    for (int a = 0; a < g.ndim; a++) { tot *= g.P[a]; if (a < al && g.Kd[a] > 512) return false; }
+    for (int a = 0; a < g.ndim; a++) { tot *= g.P[a]; if (a < al && g.Kd[a] > (f64 ? 128 : 512)) return false; }
     if (tot < (g.ndim == 1 ? 512 : 16384)) return false;
     // the row kernels decode work indices in 32 bits: rows (tile overlap inflates by < 2x per axis) x last-axis tiles must fit
     double work = (double)(g.P[al] / 128 + 2);
@@ -116,7 +126,8 @@ static int make_plan(const Geom &g, FftPlan *pl, int64_t batch = 1)
     pl->fast = fast_eligible(g);
     for (int a = 0; a < N; a++) {
         if (pl->fast) {
-            static const int menu_last[4] = {256, 512, 1024, 2048}, menu_last_cx[4] = {128, 256, 512, 1024}, menu_col[7] = {16, 32, 64, 128, 256, 512, 1024};
+            const int *menu_last, *menu_col; int n_last, n_col;
+            fast_menus(g.dtype, &menu_last, &n_last, &menu_col, &n_col);
             pl->tl[a].F = 0;
             // problems of fewer than 1.28 M padded samples are well under one wave of row warps: the shortest tile within 10 % of the
             // fewest samples (measured: c2 31.0 -> 27.3 us, c3 36.9 -> 33.3, c3 Complex 32.0 -> 30.7; 25 %: c2 26.6, c3 35.8 / 34.7;
@@ -126,10 +137,10 @@ static int make_plan(const Geom &g, FftPlan *pl, int64_t batch = 1)
             static const double small_k = getenv("NDCONV_TILE_SMALL_K") ? atof(getenv("NDCONV_TILE_SMALL_K")) : 1280.0;
             double tot = (double)batch; for (int b = 0; b < N; b++) tot *= (double)g.P[b];
             const double slack = tot < small_k * 1000.0 ? slack_env : -1.0;
-            if (a == N - 1) fast_pick_tile(g.P[a], g.Kd[a], is_cx ? menu_last_cx : menu_last, 4, &pl->tl[a], slack);
-            else fast_pick_tile(g.P[a], g.Kd[a], menu_col, 7, &pl->tl[a], slack);
+            if (a == N - 1) fast_pick_tile(g.P[a], g.Kd[a], menu_last, n_last, &pl->tl[a], slack);
+            else fast_pick_tile(g.P[a], g.Kd[a], menu_col, n_col, &pl->tl[a], slack);
             if (pl->tl[a].F == 0) { pl->fast = false; a = -1; continue; }      // no usable tile: replan everything on the generic path
-            if (!factor_radices(a == N - 1 && !is_cx ? pl->tl[a].F / 2 : pl->tl[a].F, &pl->fl[a])) return NDCONV_ERR_INTERNAL;
+            if (!factor_radices(a == N - 1 && !is_cx ? pl->tl[a].F / 2 : pl->tl[a].F, &pl->fl[a], is_dbl ? 16 : 32)) return NDCONV_ERR_INTERNAL;   // (the kernel spectrum is built by the generic kernels: f64 plans stop at radix 16)
             continue;
         }
         const bool last = (a == N - 1);
@@ -195,7 +206,7 @@ static void plan_axis0_split(const ndconv_problem *pr, const Geom &g, const FftP
     //  (2) the tail: the last tile row is mostly padding, part B gets a shorter tile.
     static const double budget = getenv("NDCONV_WS_BUDGET_MB") ? atof(getenv("NDCONV_WS_BUDGET_MB")) * 1048576.0 : 24.0 * 1073741824.0;
     const int al = g.ndim - 1;
-    double ws_tile_row = 8.0 * (pl.is_cx ? (double)pl.tl[al].F : (double)(pl.tl[al].F / 2 + 8)) * (double)pl.tl[al].ntiles;
+    double ws_tile_row = (g.dtype == NDCONV_F64 ? 16.0 : 8.0) * (pl.is_cx ? (double)pl.tl[al].F : (double)(pl.tl[al].F / 2 + 8)) * (double)pl.tl[al].ntiles;
     for (int a = 0; a < al; a++) ws_tile_row *= (double)pl.tl[a].F * (a > 0 ? (double)pl.tl[a].ntiles : 1.0);
     int64_t m = t.ntiles - 1;
     const bool over_budget = ws_tile_row * (double)t.ntiles > budget;
@@ -209,9 +220,10 @@ static void plan_axis0_split(const ndconv_problem *pr, const Geom &g, const FftP
     const int64_t rowsB = g.n[0] - (pB - g.pf[0]);
     if (rowsB < 1 || g.pb[0] >= rowsB || g.pf[0] >= rowsA) return;          // a border may not reach past the part that carries it
     if (!over_budget) {
-        static const int menu_col[7] = {16, 32, 64, 128, 256, 512, 1024};
+        const int *menu_last, *menu_col; int n_last, n_col;
+        fast_menus(g.dtype, &menu_last, &n_last, &menu_col, &n_col);
         AxisTiling tb; tb.F = 0;
-        fast_pick_tile(g.P[0] - pB, g.Kd[0], menu_col, 7, &tb);
+        fast_pick_tile(g.P[0] - pB, g.Kd[0], menu_col, n_col, &tb);
         if (tb.F == 0) return;
         const int64_t full = (int64_t)t.ntiles * t.F, split = (int64_t)(t.ntiles - 1) * t.F + (int64_t)tb.ntiles * tb.F;
         double samples = 1.0;

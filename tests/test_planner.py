@@ -60,7 +60,9 @@ def test_tile_identities(pkg, q):
 
 
 def test_path_selection(pkg, q):
-    assert q((300, 500), np.float64, z((5, 7), np.float64), pkg.ConvMode.Same, pkg.PaddingMode.Zeros)["path"] == "generic"       # no f64 fast path yet
+    f64 = q((300, 500), np.float64, z((5, 7), np.float64), pkg.ConvMode.Same, pkg.PaddingMode.Zeros)
+    assert f64["path"] == "fast" and f64["tile_len"][1] <= 512 and f64["tile_len"][0] <= 256                                      # f64 fast path: sixteen values per thread
+    assert q((300, 500), np.complex128, z((5, 7), np.complex128), pkg.ConvMode.Same, pkg.PaddingMode.Zeros)["path"] == "generic"  # Complex<f64>: generic kernels
     assert q((3, 4, 5, 6), np.float32, z((2, 2, 2, 2)), pkg.ConvMode.Same, pkg.PaddingMode.Zeros)["path"] == "generic"           # rank 4
     long1 = q((100000,), np.float32, z((9001,)), pkg.ConvMode.Valid, pkg.PaddingMode.Zeros)                                      # kernel longer than one FFT tile:
     assert long1["path"] == "split" and long1["n_tiles"] == [3] and long1["tile_valid"] == [4096]                                # cut into segments of <= cap / 2 taps
