@@ -349,12 +349,12 @@ static bool value_is_zero(const ndconv_border &b, int es)
     return true;
 }
 
-template <class T>
+template <class T, int S2 = 0, int D2 = 0>
 static int launch_direct_tile(ndconv_processor *p, const CUtensorMap &tm, const tile::TileParams &tp, int64_t grid, size_t smem, double alg_bytes)
 {
-    NDC_ONCE_PER_DEVICE(CU_CHECK(cudaFuncSetAttribute(tile::direct_tile_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)));
+    NDC_ONCE_PER_DEVICE(CU_CHECK(cudaFuncSetAttribute(tile::direct_tile_kernel<T, S2, D2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)));
     const stream_t stm = p->stream;
-    return launch_raw(p->lc(), tp.use_tma ? "direct_conv_tile_tma" : "direct_conv_tile", alg_bytes,
+    return launch_raw(p->lc(), tp.use_tma ? (S2 ? "direct_conv_tile_tma_blocked" : "direct_conv_tile_tma") : (S2 ? "direct_conv_tile_blocked" : "direct_conv_tile"), alg_bytes,
                       [&] {
                           static const bool no_pdl = getenv("NDCONV_DISABLE_PDL") != nullptr;
                           cudaLaunchConfig_t cfg = {};
@@ -362,8 +362,19 @@ static int launch_direct_tile(ndconv_processor *p, const CUtensorMap &tm, const 
                           cudaLaunchAttribute at[1];
                           at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
                           cfg.attrs = at; cfg.numAttrs = no_pdl ? 0 : 1;
-                          cudaLaunchKernelEx(&cfg, tile::direct_tile_kernel<T>, tm, tp);
+                          cudaLaunchKernelEx(&cfg, tile::direct_tile_kernel<T, S2, D2>, tm, tp);
                       });
+}
+
+// register-blocked variant: stride / dilation of the contiguous axis select the instantiation
+template <class T>
+static int launch_direct_tile_blocked(ndconv_processor *p, const CUtensorMap &tm, const tile::TileParams &tp, int64_t grid, size_t smem, double alg_bytes)
+{
+    const int s2 = (int)tp.s[2], d2 = tp.dd[2];
+    if (s2 == 1 && d2 == 1) return launch_direct_tile<T, 1, 1>(p, tm, tp, grid, smem, alg_bytes);
+    if (s2 == 2 && d2 == 1) return launch_direct_tile<T, 2, 1>(p, tm, tp, grid, smem, alg_bytes);
+    if (s2 == 1 && d2 == 2) return launch_direct_tile<T, 1, 2>(p, tm, tp, grid, smem, alg_bytes);
+    return launch_direct_tile<T, 2, 2>(p, tm, tp, grid, smem, alg_bytes);
 }
 
 // returns NDCONV_OK with *used = false when the problem is outside the tile kernel's envelope (caller falls back)
@@ -397,12 +408,19 @@ static int try_direct_tile(ndconv_processor *p, const ndconv_problem *pr, const 
     }
     if (tp.Kd[0] > (1 << 20) || tp.Kd[1] > (1 << 20) || tp.Kd[2] > (1 << 20)) return NDCONV_OK;
     tp.ostr[2] = 1; tp.ostr[1] = tp.O[2]; tp.ostr[0] = tp.O[1] * tp.O[2];
+    // register-blocked variant (kernels_direct_tile.cuh): 4- and 8-byte real elements, stride and dilation 1 or 2 and at most 8 taps along the
+    // contiguous axis; every thread owns 4 neighbouring outputs there
+    static const bool no_blocked = getenv("NDCONV_DISABLE_BLOCKED") != nullptr;
+    static const int64_t blocked_min_out = getenv("NDCONV_BLOCKED_MIN_OUT") ? atoll(getenv("NDCONV_BLOCKED_MIN_OUT")) : (4ll << 20);   // tests lower it to reach the variant with small arrays
+    for (int a3 = 0; a3 < 3; a3++) { const int a = a3 - sh; tp.kk[a3] = a < 0 ? 1 : (int)g.k[a]; tp.dd[a3] = a < 0 ? 1 : (int)g.d[a]; }
+    const bool blk_type = g.dtype == NDCONV_I32 || g.dtype == NDCONV_U32 || g.dtype == NDCONV_F32 || g.dtype == NDCONV_I64 || g.dtype == NDCONV_U64 || g.dtype == NDCONV_F64;
+    // ... in the throughput regime only (at least 4 M outputs): a small problem is one wave of latency, which the blocked variant's larger
+    // windows make worse (c4: 19 -> 71 us), a large one is bound by shared-memory reads per multiply-add, which it cuts 2-3 x
+    const bool blocked = !no_blocked && blk_type && (tp.s[2] == 1 || tp.s[2] == 2) && (tp.dd[2] == 1 || tp.dd[2] == 2) && tp.kk[2] <= tile::kRowTaps &&
+                         (int64_t)tp.kk[0] * tp.kk[1] <= 1024 && tp.O[2] >= 64 && tp.O[1] >= 16 && g.out_total >= blocked_min_out;
+    tp.nrow = blocked ? tp.kk[0] * tp.kk[1] : 0;
     // tile shape
     auto np2 = [](int64_t v) { int r = 1; while (r < v && r < 256) r <<= 1; return r; };
-    int TO2 = np2(tp.O[2]);
-    while (TO2 > 32 && (tile::kThreads / TO2) < std::min<int64_t>(tp.O[1], 8)) TO2 >>= 1;
-    int TO1 = (int)std::min<int64_t>(tile::kThreads / TO2, np2(tp.O[1]));
-    int TO0 = (int)std::min<int64_t>(tile::kMaxTO0, tp.O[0]);
     const int round = 16 / std::min(es, 16);
     auto shape = [&](int T0, int T1, int T2) {
         tp.TO[0] = T0; tp.TO[1] = T1; tp.TO[2] = T2;
@@ -410,13 +428,32 @@ static int try_direct_tile(ndconv_processor *p, const ndconv_problem *pr, const 
         tp.IT2p = (tp.IT[2] + (round - 1) + round - 1) / round * round;   // + (round-1): room for the per-tile alignment shift
         return (int64_t)tp.IT[0] * tp.IT[1] * tp.IT2p;
     };
-    int64_t elems = shape(TO0, TO1, TO2);
-    const int64_t budget = 150 * 1024;
-    while (elems * es > budget && TO0 > 1) { TO0--; elems = shape(TO0, TO1, TO2); }
-    while (elems * es > budget && TO1 > 1) { TO1 >>= 1; elems = shape(TO0, TO1, TO2); }
-    while (elems * es > budget && TO2 > 1) { TO2 >>= 1; elems = shape(TO0, TO1, TO2); }
-    if (elems * es > budget) return NDCONV_OK;
-    const size_t tap_bytes = align_up((size_t)e.ntap * es, 16) + (size_t)e.ntap * 4 + (size_t)(tp.IT[0] + tp.IT[1] + tp.IT2p) * 4;   // taps + the window's border maps
+    int64_t elems;
+    if (blocked) {
+        // 16 x 16 threads, 4 outputs each along the contiguous axis: 16 x 64 outputs per plane; 4, 2 or 1 planes so that two CTAs share an SM
+        int TO0 = 4;
+        while (TO0 > tp.O[0] && TO0 > 1) TO0 >>= 1;
+        elems = shape(TO0, 16, 64);
+        while (elems * es > 100 * 1024 && TO0 > 1) { TO0 >>= 1; elems = shape(TO0, 16, 64); }
+        if (elems * es > 100 * 1024 || tp.IT2p > 256 || tp.IT[1] > 256) { tp.nrow = 0; }
+    }
+    const bool use_blocked = blocked && tp.nrow > 0;
+    if (use_blocked && getenv("NDCONV_DEBUG_BLOCKED")) fprintf(stderr, "[ndconv] blocked direct conv: tile (%d, %d, %d) outputs, stride %d, dilation %d, %d kernel rows\n", tp.TO[0], tp.TO[1], tp.TO[2], (int)tp.s[2], tp.dd[2], tp.nrow);
+    if (!use_blocked) {
+        tp.nrow = 0;
+        int TO2 = np2(tp.O[2]);
+        while (TO2 > 32 && (tile::kThreads / TO2) < std::min<int64_t>(tp.O[1], 8)) TO2 >>= 1;
+        int TO1 = (int)std::min<int64_t>(tile::kThreads / TO2, np2(tp.O[1]));
+        int TO0 = (int)std::min<int64_t>(tile::kMaxTO0, tp.O[0]);
+        elems = shape(TO0, TO1, TO2);
+        const int64_t budget = 150 * 1024;
+        while (elems * es > budget && TO0 > 1) { TO0--; elems = shape(TO0, TO1, TO2); }
+        while (elems * es > budget && TO1 > 1) { TO1 >>= 1; elems = shape(TO0, TO1, TO2); }
+        while (elems * es > budget && TO2 > 1) { TO2 >>= 1; elems = shape(TO0, TO1, TO2); }
+        if (elems * es > budget) return NDCONV_OK;
+    }
+    const size_t tap_bytes = align_up((size_t)e.ntap * es, 16) + (size_t)e.ntap * 4 + (size_t)(tp.IT[0] + tp.IT[1] + tp.IT2p) * 4 +   // taps + the window's border maps
+                             (size_t)tp.nrow * 8 + 16 + (size_t)tp.nrow * tile::kRowTaps * es;                                          // + the dense kernel rows of the blocked variant
     const size_t tile_bytes = align_up((size_t)elems * es, 128);
     if (tile_bytes + tap_bytes + 256 > 190 * 1024) return NDCONV_OK;
     tp.tile_elems = (int)elems;
@@ -450,11 +487,11 @@ static int try_direct_tile(ndconv_processor *p, const ndconv_problem *pr, const 
     switch (g.dtype) {
     case NDCONV_I8: case NDCONV_U8: st = launch_direct_tile<uint8_t>(p, tm, tp, grid, smem, alg_bytes); break;
     case NDCONV_I16: case NDCONV_U16: st = launch_direct_tile<uint16_t>(p, tm, tp, grid, smem, alg_bytes); break;
-    case NDCONV_I32: case NDCONV_U32: st = launch_direct_tile<uint32_t>(p, tm, tp, grid, smem, alg_bytes); break;
-    case NDCONV_I64: case NDCONV_U64: st = launch_direct_tile<uint64_t>(p, tm, tp, grid, smem, alg_bytes); break;
+    case NDCONV_I32: case NDCONV_U32: st = use_blocked ? launch_direct_tile_blocked<uint32_t>(p, tm, tp, grid, smem, alg_bytes) : launch_direct_tile<uint32_t>(p, tm, tp, grid, smem, alg_bytes); break;
+    case NDCONV_I64: case NDCONV_U64: st = use_blocked ? launch_direct_tile_blocked<uint64_t>(p, tm, tp, grid, smem, alg_bytes) : launch_direct_tile<uint64_t>(p, tm, tp, grid, smem, alg_bytes); break;
     case NDCONV_I128: case NDCONV_U128: st = launch_direct_tile<u128_t>(p, tm, tp, grid, smem, alg_bytes); break;
-    case NDCONV_F32: st = launch_direct_tile<float>(p, tm, tp, grid, smem, alg_bytes); break;
-    case NDCONV_F64: st = launch_direct_tile<double>(p, tm, tp, grid, smem, alg_bytes); break;
+    case NDCONV_F32: st = use_blocked ? launch_direct_tile_blocked<float>(p, tm, tp, grid, smem, alg_bytes) : launch_direct_tile<float>(p, tm, tp, grid, smem, alg_bytes); break;
+    case NDCONV_F64: st = use_blocked ? launch_direct_tile_blocked<double>(p, tm, tp, grid, smem, alg_bytes) : launch_direct_tile<double>(p, tm, tp, grid, smem, alg_bytes); break;
     case NDCONV_C32: st = launch_direct_tile<cx<float>>(p, tm, tp, grid, smem, alg_bytes); break;
     case NDCONV_C64: st = launch_direct_tile<cx<double>>(p, tm, tp, grid, smem, alg_bytes); break;
     default: return NDCONV_OK;

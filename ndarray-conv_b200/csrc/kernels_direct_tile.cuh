@@ -27,6 +27,8 @@ namespace tile {
 
 constexpr int kThreads = 256;
 constexpr int kMaxTO0 = 4;
+constexpr int kBlockR = 4;               // register-blocked variant: outputs per thread along the contiguous axis
+constexpr int kRowTaps = 8;              //   ... and the longest kernel row it takes
 
 struct TileParams {
     // geometry embedded in 3-D (axis 2 = contiguous)
@@ -43,6 +45,9 @@ struct TileParams {
     const void *x;
     void *out;
     int tile_elems;
+    // register-blocked variant (direct_tile_kernel<T, S2, D2>): kernel extents and dilations (embedded in 3-D) and the kernel rows
+    int kk[3], dd[3];
+    int nrow;                            // kk[0] * kk[1] kernel rows of up to kRowTaps taps along the contiguous axis
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -79,7 +84,71 @@ __device__ __forceinline__ void tap_loop(uint32_t tile_addr, const T *s_w, const
     }
 }
 
-template <class T>
+
+// Register-blocked tap loop (stride S2 and dilation D2 of the contiguous axis are compile-time, 1 or 2): a thread owns NQ x R
+// outputs (NQ along axis 0, R = 4 neighbours along the contiguous axis).  Per kernel ROW it loads, for each of its NQ planes, the
+// (R - 1) S2 + (k2 - 1) D2 + 1 samples its R outputs share ONCE into registers, as 16-byte vectors (consecutive lanes read consecutive
+// 16- or 32-byte chunks: no bank conflicts; scalar reads at that lane stride were 4- to 8-way conflicted and SLOWER than the plain
+// tap loop), and the row's weights once -- instead of one shared-memory read per multiply-add.  SHIFT is the tile's alignment shift
+// (the TMA box starts on a 16-byte boundary, kernels_direct_tile.cuh header), a compile-time constant here so that the samples keep
+// static register indices.  Every output still sees its taps in the reference's order (rows ascending, taps of a row ascending, zero
+// weights skipped: gen_offset_list, src/dilation/mod.rs:34-60) with un-fused multiply / add, so results stay bit-identical.
+template <class T, int NQ, int S2, int D2, int SHIFT>
+__device__ __forceinline__ void blocked_loop(uint32_t tile_addr16, const T *s_rw, const int32_t *s_roff, const uint32_t *s_rmask, int nrow, int k2, int step0_bytes,
+                                             T (*acc)[kBlockR])
+{
+    constexpr int R = kBlockR, VN = 16 / (int)sizeof(T), SEG = (R - 1) * S2 + (kRowTaps - 1) * D2 + 1, NV = (SHIFT + SEG + VN - 1) / VN;
+    const int nv = (SHIFT + (R - 1) * S2 + (k2 - 1) * D2 + 1 + VN - 1) / VN;
+#pragma unroll
+    for (int q = 0; q < NQ; q++)
+#pragma unroll
+        for (int j = 0; j < R; j++) acc[q][j] = Elem<T>::zero();
+    for (int r = 0; r < nrow; r++) {
+        const uint32_t mask = s_rmask[r];
+        if (!mask) continue;                                  // a kernel row of zero weights
+        T w[kRowTaps];
+#pragma unroll
+        for (int v = 0; v < kRowTaps; v++) w[v] = s_rw[r * kRowTaps + v];
+        uint32_t a = tile_addr16 + (uint32_t)s_roff[r];
+#pragma unroll
+        for (int q = 0; q < NQ; q++) {
+            T buf[NV * VN];
+#pragma unroll
+            for (int c = 0; c < NV; c++) {
+                ulonglong2 raw = make_ulonglong2(0ull, 0ull);
+                if (c < nv) raw = LdsRaw<16>::ld(a + 16u * (uint32_t)c);
+                memcpy(&buf[c * VN], &raw, 16);
+            }
+#pragma unroll
+            for (int v = 0; v < kRowTaps; v++) {
+                if ((mask >> v) & 1u) {
+#pragma unroll
+                    for (int j = 0; j < R; j++) acc[q][j] = Elem<T>::mac(acc[q][j], buf[SHIFT + j * S2 + v * D2], w[v]);
+                }
+            }
+            a += (uint32_t)step0_bytes;
+        }
+    }
+}
+template <class T, int NQ, int S2, int D2>
+__device__ __forceinline__ void blocked_loop_shift(int shift, uint32_t tile_addr16, const T *s_rw, const int32_t *s_roff, const uint32_t *s_rmask, int nrow, int k2,
+                                                   int step0_bytes, T (*acc)[kBlockR])
+{
+    if constexpr (sizeof(T) == 8) {
+        if (shift == 0) blocked_loop<T, NQ, S2, D2, 0>(tile_addr16, s_rw, s_roff, s_rmask, nrow, k2, step0_bytes, acc);
+        else blocked_loop<T, NQ, S2, D2, 1>(tile_addr16, s_rw, s_roff, s_rmask, nrow, k2, step0_bytes, acc);
+    } else {
+        switch (shift) {
+        case 0: blocked_loop<T, NQ, S2, D2, 0>(tile_addr16, s_rw, s_roff, s_rmask, nrow, k2, step0_bytes, acc); break;
+        case 1: blocked_loop<T, NQ, S2, D2, 1>(tile_addr16, s_rw, s_roff, s_rmask, nrow, k2, step0_bytes, acc); break;
+        case 2: blocked_loop<T, NQ, S2, D2, 2>(tile_addr16, s_rw, s_roff, s_rmask, nrow, k2, step0_bytes, acc); break;
+        default: blocked_loop<T, NQ, S2, D2, 3>(tile_addr16, s_rw, s_roff, s_rmask, nrow, k2, step0_bytes, acc); break;
+        }
+    }
+}
+
+// S2 == 0: one output column per thread, the compacted tap list (any stride / dilation / kernel extent); S2 > 0: the register-blocked rows above
+template <class T, int S2 = 0, int D2 = 0>
 __global__ void __launch_bounds__(kThreads) direct_tile_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TileParams p)
 {
     // programmatic dependent launch (see kernels_fft_fast.cuh): the next kernel of the stream may start now; this one stages
@@ -187,6 +256,25 @@ __global__ void __launch_bounds__(kThreads) direct_tile_kernel(const __grid_cons
         s_off[t] = off * (int)sizeof(T);           // byte offset inside the tile
         s_w[t] = ((const T *)p.tap_w)[t];
     }
+    // register-blocked variant: the kernel as dense rows (row = position on the two outer axes; tap v of a row sits at dilated offset v * D2)
+    int32_t *s_roff = s_map2 + row_elems;
+    uint32_t *s_rmask = reinterpret_cast<uint32_t *>(s_roff + p.nrow);
+    T *s_rw = reinterpret_cast<T *>((reinterpret_cast<uintptr_t>(s_rmask + p.nrow) + 15) & ~(uintptr_t)15);
+    if constexpr (S2 > 0) {
+        for (int r = tid; r < p.nrow; r += kThreads) {
+            s_roff[r] = ((r / p.kk[1]) * p.dd[0] * plane_elems + (r % p.kk[1]) * p.dd[1] * row_elems) * (int)sizeof(T);
+            s_rmask[r] = 0u;
+        }
+        for (int e = tid; e < p.nrow * kRowTaps; e += kThreads) s_rw[e] = Elem<T>::zero();
+        __syncthreads();
+        for (int t = tid; t < p.ntap; t += kThreads) {
+            const int32_t *o = p.tap_off + t * NDC_MAX_DIM;
+            const int u0 = p.axis_shift <= 0 ? o[0 - p.axis_shift] / p.dd[0] : 0, u1 = p.axis_shift <= 1 ? o[1 - p.axis_shift] / p.dd[1] : 0, v = o[2 - p.axis_shift] / p.dd[2];
+            const int r = u0 * p.kk[1] + u1;
+            s_rw[r * kRowTaps + v] = ((const T *)p.tap_w)[t];
+            atomicOr(&s_rmask[r], 1u << v);
+        }
+    }
     __syncthreads();
     auto ident_col = [&](int h) { return h; };
     if (!tma_ok) {
@@ -220,26 +308,57 @@ __global__ void __launch_bounds__(kThreads) direct_tile_kernel(const __grid_cons
             __syncthreads();
         }
     }
-    // compute: thread -> (o1, o2) of the tile, TO0 accumulators in registers
-    const int o2l = tid % p.TO[2], o1l = tid / p.TO[2];
-    if (o1l < p.TO[1]) {
-        const int64_t o1 = (int64_t)t1 * p.TO[1] + o1l, o2 = (int64_t)t2 * p.TO[2] + o2l;
-        T acc[kMaxTO0];
-        const int base = o1l * (int)p.s[1] * row_elems + o2l * (int)p.s[2] + shift2;
-        const uint32_t tile_addr = smem_u32(tile) + (uint32_t)base * (uint32_t)sizeof(T);
-        const int step0_bytes = (int)p.s[0] * plane_elems * (int)sizeof(T);
-        switch (p.TO[0]) {
-        case 1: tap_loop<T, 1>(tile_addr, s_w, s_off, p.ntap, step0_bytes, acc); break;
-        case 2: tap_loop<T, 2>(tile_addr, s_w, s_off, p.ntap, step0_bytes, acc); break;
-        case 3: tap_loop<T, 3>(tile_addr, s_w, s_off, p.ntap, step0_bytes, acc); break;
-        default: tap_loop<T, 4>(tile_addr, s_w, s_off, p.ntap, step0_bytes, acc); break;
-        }
-        if (o1 < p.O[1] && o2 < p.O[2]) {
-            T *out = (T *)p.out;
+    // compute
+    if constexpr (S2 > 0) {
+        // thread -> (o1, four neighbouring o2) of the tile, TO0 x 4 accumulators in registers
+        const int T2 = p.TO[2] / kBlockR;
+        const int o2l = (tid % T2) * kBlockR, o1l = tid / T2;
+        if (o1l < p.TO[1]) {
+            const int64_t o1 = (int64_t)t1 * p.TO[1] + o1l, o2 = (int64_t)t2 * p.TO[2] + o2l;
+            T acc[kMaxTO0][kBlockR];
+            const int base = o1l * (int)p.s[1] * row_elems + o2l * S2;          // 16-byte aligned; the tile's alignment shift is a template constant of the loop
+            const uint32_t tile_addr16 = smem_u32(tile) + (uint32_t)base * (uint32_t)sizeof(T);
+            const int step0_bytes = (int)p.s[0] * plane_elems * (int)sizeof(T);
+            switch (p.TO[0]) {                                                   // the host picks 1, 2 or 4 outputs along axis 0 for this variant
+            case 1: blocked_loop_shift<T, 1, S2, D2>(shift2, tile_addr16, s_rw, s_roff, s_rmask, p.nrow, p.kk[2], step0_bytes, acc); break;
+            case 2: blocked_loop_shift<T, 2, S2, D2>(shift2, tile_addr16, s_rw, s_roff, s_rmask, p.nrow, p.kk[2], step0_bytes, acc); break;
+            default: blocked_loop_shift<T, 4, S2, D2>(shift2, tile_addr16, s_rw, s_roff, s_rmask, p.nrow, p.kk[2], step0_bytes, acc); break;
+            }
+            if (o1 < p.O[1]) {
+                T *out = (T *)p.out;
 #pragma unroll
-            for (int q = 0; q < kMaxTO0; q++) {
-                const int64_t o0 = (int64_t)t0 * p.TO[0] + q;
-                if (q < p.TO[0] && o0 < p.O[0]) out[o0 * p.ostr[0] + o1 * p.ostr[1] + o2] = acc[q];
+                for (int q = 0; q < kMaxTO0; q++) {
+                    const int64_t o0 = (int64_t)t0 * p.TO[0] + q;
+                    if (q < p.TO[0] && o0 < p.O[0]) {
+                        T *orow = out + o0 * p.ostr[0] + o1 * p.ostr[1] + o2;
+#pragma unroll
+                        for (int j = 0; j < kBlockR; j++) if (o2 + j < p.O[2]) orow[j] = acc[q][j];
+                    }
+                }
+            }
+        }
+    } else {
+        // thread -> (o1, o2) of the tile, TO0 accumulators in registers
+        const int o2l = tid % p.TO[2], o1l = tid / p.TO[2];
+        if (o1l < p.TO[1]) {
+            const int64_t o1 = (int64_t)t1 * p.TO[1] + o1l, o2 = (int64_t)t2 * p.TO[2] + o2l;
+            T acc[kMaxTO0];
+            const int base = o1l * (int)p.s[1] * row_elems + o2l * (int)p.s[2] + shift2;
+            const uint32_t tile_addr = smem_u32(tile) + (uint32_t)base * (uint32_t)sizeof(T);
+            const int step0_bytes = (int)p.s[0] * plane_elems * (int)sizeof(T);
+            switch (p.TO[0]) {
+            case 1: tap_loop<T, 1>(tile_addr, s_w, s_off, p.ntap, step0_bytes, acc); break;
+            case 2: tap_loop<T, 2>(tile_addr, s_w, s_off, p.ntap, step0_bytes, acc); break;
+            case 3: tap_loop<T, 3>(tile_addr, s_w, s_off, p.ntap, step0_bytes, acc); break;
+            default: tap_loop<T, 4>(tile_addr, s_w, s_off, p.ntap, step0_bytes, acc); break;
+            }
+            if (o1 < p.O[1] && o2 < p.O[2]) {
+                T *out = (T *)p.out;
+#pragma unroll
+                for (int q = 0; q < kMaxTO0; q++) {
+                    const int64_t o0 = (int64_t)t0 * p.TO[0] + q;
+                    if (q < p.TO[0] && o0 < p.O[0]) out[o0 * p.ostr[0] + o1 * p.ostr[1] + o2] = acc[q];
+                }
             }
         }
     }
