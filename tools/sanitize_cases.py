@@ -70,5 +70,18 @@ torch.cuda.synchronize()
 pkg.conv_fft_sharded_device(procs, (1500, 1300), np.float32, kk, pkg.ConvMode.Full, pkg.PaddingMode.Reflect, shards)
 for q in procs:
     q.synchronize(); q.close()
+# round 2b: Tensor-Memory-resident column pass (>= 10 tiles of 1024 rows: bundles, chunk hand-over between the two groups, parts through the
+# scratch buffers; one geometry with fewer chunks than CTAs and one with a single bundle), f64 fast path (rank 2 with edge tiles, rank 3,
+# strided output), register-blocked direct conv (run with NDCONV_BLOCKED_MIN_OUT=0: strides / dilations 1 and 2, 4- and 8-byte elements)
+pkg.conv_fft_with_processor(rng.random((10200, 520), dtype=np.float32), rng.random((3, 9), dtype=np.float32), pkg.ConvMode.Same, pkg.PaddingMode.Const(0.5), proc)
+pkg.conv_fft_with_processor(rng.random((12000, 1000), dtype=np.float32), rng.random((5, 5), dtype=np.float32), pkg.ConvMode.Same, pkg.PaddingMode.Replicate, proc)
+pkg.conv_fft_with_processor(rng.random((700, 1500)), rng.random((5, 9)), pkg.ConvMode.Full, pkg.PaddingMode.Reflect, proc)
+pkg.conv_fft_with_processor(rng.random((20, 70, 300)), rng.random((3, 4, 5)), pkg.ConvMode.Custom([1, 0, 5], [2, 1, 3]), pkg.PaddingMode.Custom([B.Reflect, B.Circular, B.Const(0.5)]), proc)
+pkg.conv_fft_with_processor(rng.random((140, 150)), rng.random((3, 3)), pkg.ConvMode.Same, pkg.PaddingMode.Reflect, proc)
+xb = rng.integers(-9, 9, size=(5, 40, 200), dtype=np.int32)
+pkg.conv(xb, ki, pkg.ConvMode.Custom([1, 2, 2], [2, 2, 2]), pkg.PaddingMode.Replicate, processor=proc)
+pkg.conv(xb.astype(np.int64), pkg.with_dilation(ki[:, :3, :4].astype(np.int64), 2), pkg.ConvMode.Same, pkg.PaddingMode.Circular, processor=proc)
+pkg.conv(rng.random((64, 260), dtype=np.float32), rng.random((7, 7), dtype=np.float32), pkg.ConvMode.Same, pkg.PaddingMode.Reflect, processor=proc)
+pkg.conv(rng.random((20, 150)), rng.random((3, 4)), pkg.ConvMode.Explicit([[1, 1], [3, 2]], [1, 2]), pkg.PaddingMode.Reflect, processor=proc)
 proc.close()
 print("SANITIZE_CASES_DONE")
