@@ -377,6 +377,40 @@ static int launch_direct_tile_blocked(ndconv_processor *p, const CUtensorMap &tm
     return launch_direct_tile<T, 2, 2>(p, tm, tp, grid, smem, alg_bytes);
 }
 
+// persistent variant: as many CTAs as fit the device at once, each walking tiles blockIdx.x, + gridDim.x, ... with two window buffers
+template <class T, int S2, int D2>
+static int launch_direct_persistent_sd(ndconv_processor *p, const CUtensorMap &tm, const tile::TileParams &tp, int64_t ntiles, size_t smem, double alg_bytes)
+{
+    NDC_ONCE_PER_DEVICE(CU_CHECK(cudaFuncSetAttribute(tile::direct_tile_persistent<T, S2, D2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)));
+    int per_sm = 0;
+    CU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tile::direct_tile_persistent<T, S2, D2>, tile::kThreads, smem));
+    if (per_sm < 1) per_sm = 1;
+    static const int max_grid = getenv("NDCONV_PERSIST_MAX_GRID") ? atoi(getenv("NDCONV_PERSIST_MAX_GRID")) : 0;      // tests: few CTAs, many tiles each
+    int grid = (int)std::min<int64_t>(ntiles, (int64_t)p->num_sms * per_sm);
+    if (max_grid > 0) grid = std::min(grid, max_grid);
+    if (getenv("NDCONV_DEBUG_BLOCKED")) fprintf(stderr, "[ndconv] persistent direct conv: %lld tiles on %d CTAs (%d per SM)\n", (long long)ntiles, grid, per_sm);
+    const stream_t stm = p->stream;
+    return launch_raw(p->lc(), "direct_conv_tile_tma_persistent", alg_bytes,
+                      [&] {
+                          static const bool no_pdl = getenv("NDCONV_DISABLE_PDL") != nullptr;
+                          cudaLaunchConfig_t cfg = {};
+                          cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(tile::kThreads); cfg.dynamicSmemBytes = smem; cfg.stream = stm;
+                          cudaLaunchAttribute at[1];
+                          at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
+                          cfg.attrs = at; cfg.numAttrs = no_pdl ? 0 : 1;
+                          cudaLaunchKernelEx(&cfg, tile::direct_tile_persistent<T, S2, D2>, tm, tp, (int)ntiles);
+                      });
+}
+template <class T>
+static int launch_direct_persistent(ndconv_processor *p, const CUtensorMap &tm, const tile::TileParams &tp, int64_t ntiles, size_t smem, double alg_bytes)
+{
+    const int s2 = (int)tp.s[2], d2 = tp.dd[2];
+    if (s2 == 1 && d2 == 1) return launch_direct_persistent_sd<T, 1, 1>(p, tm, tp, ntiles, smem, alg_bytes);
+    if (s2 == 2 && d2 == 1) return launch_direct_persistent_sd<T, 2, 1>(p, tm, tp, ntiles, smem, alg_bytes);
+    if (s2 == 1 && d2 == 2) return launch_direct_persistent_sd<T, 1, 2>(p, tm, tp, ntiles, smem, alg_bytes);
+    return launch_direct_persistent_sd<T, 2, 2>(p, tm, tp, ntiles, smem, alg_bytes);
+}
+
 // returns NDCONV_OK with *used = false when the problem is outside the tile kernel's envelope (caller falls back)
 static int try_direct_tile(ndconv_processor *p, const ndconv_problem *pr, const PlanEntry &e, const void *dev_x, void *dev_out, bool *used)
 {
@@ -431,10 +465,16 @@ static int try_direct_tile(ndconv_processor *p, const ndconv_problem *pr, const 
     int64_t elems;
     if (blocked) {
         // 16 x 16 threads, 4 outputs each along the contiguous axis: 16 x 64 outputs per plane; 4, 2 or 1 planes so that two CTAs share an SM
+        // (windows of at most 48 KB are preferred: two of them fit one CTA of the persistent variant, two such CTAs one SM)
         int TO0 = 4;
         while (TO0 > tp.O[0] && TO0 > 1) TO0 >>= 1;
+        const int TO0max = TO0;
         elems = shape(TO0, 16, 64);
-        while (elems * es > 100 * 1024 && TO0 > 1) { TO0 >>= 1; elems = shape(TO0, 16, 64); }
+        while (elems * es > 48 * 1024 && TO0 > 1) { TO0 >>= 1; elems = shape(TO0, 16, 64); }
+        if (elems * es > 48 * 1024) {
+            TO0 = TO0max; elems = shape(TO0, 16, 64);
+            while (elems * es > 100 * 1024 && TO0 > 1) { TO0 >>= 1; elems = shape(TO0, 16, 64); }
+        }
         if (elems * es > 100 * 1024 || tp.IT2p > 256 || tp.IT[1] > 256) { tp.nrow = 0; }
     }
     const bool use_blocked = blocked && tp.nrow > 0;
@@ -484,6 +524,24 @@ static int try_direct_tile(ndconv_processor *p, const ndconv_problem *pr, const 
     tp.use_tma = tma ? 1 : 0;
     const size_t smem = tile_bytes + tap_bytes + 128;
     const double alg_bytes = (double)es * ((double)g.data_total + (double)g.out_total + (double)e.ntap);
+    static const bool no_persist = getenv("NDCONV_DISABLE_PERSIST") != nullptr;
+    static const int64_t persist_min_tiles = getenv("NDCONV_PERSIST_MIN_TILES") ? atoll(getenv("NDCONV_PERSIST_MIN_TILES")) : -1;
+    // measured (profiles/r02d_*): two window buffers per CTA win on rank-2 problems (8192^2 k = 7x7 f32 666 -> 616 us, 4096^2 k = 5x5 dilation 2 f64
+    // 281 -> 210 us) and lose 5-13 % on rank 3, where the TMA boxes of 4 output planes re-read 6 input planes and box traffic, not latency, is the
+    // bound; the tests force it onto rank 3 as well (NDCONV_PERSIST_MIN_TILES=0)
+    const bool persist_rank = persist_min_tiles >= 0 || tp.n[0] == 1;
+    if (use_blocked && tma && !no_persist && persist_rank && 2 * tile_bytes + tap_bytes + 256 <= 100 * 1024 && grid >= (persist_min_tiles >= 0 ? persist_min_tiles : 4 * (int64_t)p->num_sms)) {
+        const size_t smem2 = 2 * tile_bytes + tap_bytes + 128;
+        switch (g.dtype) {
+        case NDCONV_I32: case NDCONV_U32: st = launch_direct_persistent<uint32_t>(p, tm, tp, grid, smem2, alg_bytes); break;
+        case NDCONV_I64: case NDCONV_U64: st = launch_direct_persistent<uint64_t>(p, tm, tp, grid, smem2, alg_bytes); break;
+        case NDCONV_F32: st = launch_direct_persistent<float>(p, tm, tp, grid, smem2, alg_bytes); break;
+        default: st = launch_direct_persistent<double>(p, tm, tp, grid, smem2, alg_bytes); break;
+        }
+        if (st) return st;
+        *used = true;
+        return NDCONV_OK;
+    }
     switch (g.dtype) {
     case NDCONV_I8: case NDCONV_U8: st = launch_direct_tile<uint8_t>(p, tm, tp, grid, smem, alg_bytes); break;
     case NDCONV_I16: case NDCONV_U16: st = launch_direct_tile<uint16_t>(p, tm, tp, grid, smem, alg_bytes); break;

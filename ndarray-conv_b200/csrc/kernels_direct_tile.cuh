@@ -186,13 +186,18 @@ __global__ void __launch_bounds__(kThreads) direct_tile_kernel(const __grid_cons
 
     // window maps in shared memory: s_map[a][i] = border map of padded coordinate c_lo[a] + i (kBeyond outside [0, P[a]))
     constexpr int32_t kBeyond = INT32_MIN;
+    // (staged after the TMA box has been issued, and only by the tiles that gather or patch through them: the dependent global loads of the
+    // maps used to sit in front of every tile's box load)
     int32_t *s_map0 = s_off + p.ntap, *s_map1 = s_map0 + p.IT[0], *s_map2 = s_map1 + p.IT[1];
-    for (int e = tid; e < p.IT[0] + p.IT[1] + row_elems; e += kThreads) {
-        const int a = e < p.IT[0] ? 0 : (e < p.IT[0] + p.IT[1] ? 1 : 2);
-        const int i = e - (a == 0 ? 0 : (a == 1 ? p.IT[0] : p.IT[0] + p.IT[1]));
-        const int64_t c = (a == 2 ? c2_lo : c_lo[a]) + i;
-        s_map0[e] = (c < 0 || c >= p.P[a]) ? kBeyond : p.map[a][c];
-    }
+    auto stage_maps = [&]() {
+        for (int e = tid; e < p.IT[0] + p.IT[1] + row_elems; e += kThreads) {
+            const int a = e < p.IT[0] ? 0 : (e < p.IT[0] + p.IT[1] ? 1 : 2);
+            const int i = e - (a == 0 ? 0 : (a == 1 ? p.IT[0] : p.IT[0] + p.IT[1]));
+            const int64_t c = (a == 2 ? c2_lo : c_lo[a]) + i;
+            s_map0[e] = (c < 0 || c >= p.P[a]) ? kBeyond : p.map[a][c];
+        }
+    };
+    if (!tma_ok) stage_maps();
     // value of the padded array at window element (i0, i1, i2): the highest-numbered constant axis wins, never-written cells
     // and the 16-byte rounding slack read 0 (same precedence as the sequential padding of src/padding/mod.rs:119-153)
     auto resolve = [&](int i0, int i1, int i2) -> T {
@@ -246,6 +251,7 @@ __global__ void __launch_bounds__(kThreads) direct_tile_kernel(const __grid_cons
                 : "memory");
         }
     }
+    if (tma_ok && need_patch) stage_maps();
     // taps -> shared memory: (byte offset inside the tile, weight), reference order
     for (int t = tid; t < p.ntap; t += kThreads) {
         const int32_t *o = p.tap_off + t * NDC_MAX_DIM;
@@ -361,6 +367,189 @@ __global__ void __launch_bounds__(kThreads) direct_tile_kernel(const __grid_cons
                 }
             }
         }
+    }
+}
+
+
+// ---- persistent variant: one CTA walks many tiles, two window buffers ---------------------------------------------------------------
+// In the throughput regime (65 536 tiles of a 256 x 1024 x 1024 array) one CTA per tile pays the whole latency chain per tile -- window
+// maps, TMA box, tap staging, barrier, compute, store -- with four CTAs per SM to overlap it: the large 3-D shapes ran at 0.7-1.2 TB/s of
+// compulsory bytes while neither HBM nor the multiply-adds were busy.  Here a CTA stages the kernel rows ONCE, then loops over tiles
+// n = blockIdx.x, + gridDim.x, ...: the TMA box of tile n + gridDim.x is issued into the other buffer before tile n is computed
+// (mbarrier per buffer), the window's border maps are staged only for the edge tiles that need a halo patch.  Register-blocked compute
+// (blocked_loop) only; everything else about a tile is direct_tile_kernel's.
+template <class T, int S2, int D2>
+__global__ void __launch_bounds__(kThreads) direct_tile_persistent(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TileParams p, int ntiles_total)
+{
+    asm volatile("griddepcontrol.launch_dependents;");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int tile_bytes = (p.tile_elems * (int)sizeof(T) + 127) & ~127;
+    unsigned char *tables = smem_raw + 2 * tile_bytes;
+    int32_t *s_map0 = reinterpret_cast<int32_t *>(tables), *s_map1 = s_map0 + p.IT[0], *s_map2 = s_map1 + p.IT[1];
+    const int row_elems = p.IT2p, plane_elems = p.IT[1] * p.IT2p;
+    int32_t *s_roff = s_map2 + row_elems;
+    uint32_t *s_rmask = reinterpret_cast<uint32_t *>(s_roff + p.nrow);
+    T *s_rw = reinterpret_cast<T *>((reinterpret_cast<uintptr_t>(s_rmask + p.nrow) + 15) & ~(uintptr_t)15);
+    __shared__ __align__(8) uint64_t mbar[2];
+    const int tid = threadIdx.x;
+    constexpr int32_t kBeyond = INT32_MIN;
+    constexpr int kAlign = 16 / (int)sizeof(T);
+
+    // kernel rows (plan constants: before the wait on the predecessors)
+    for (int r = tid; r < p.nrow; r += kThreads) {
+        s_roff[r] = ((r / p.kk[1]) * p.dd[0] * plane_elems + (r % p.kk[1]) * p.dd[1] * row_elems) * (int)sizeof(T);
+        s_rmask[r] = 0u;
+    }
+    for (int e = tid; e < p.nrow * kRowTaps; e += kThreads) s_rw[e] = Elem<T>::zero();
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar[0])));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar[1])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    for (int t = tid; t < p.ntap; t += kThreads) {
+        const int32_t *o = p.tap_off + t * NDC_MAX_DIM;
+        const int u0 = p.axis_shift <= 0 ? o[0 - p.axis_shift] / p.dd[0] : 0, u1 = p.axis_shift <= 1 ? o[1 - p.axis_shift] / p.dd[1] : 0, v = o[2 - p.axis_shift] / p.dd[2];
+        const int r = u0 * p.kk[1] + u1;
+        s_rw[r * kRowTaps + v] = ((const T *)p.tap_w)[t];
+        atomicOr(&s_rmask[r], 1u << v);
+    }
+    struct TileGeo { int t0, t1, t2, shift2; int64_t c0, c1, c2, c2_lo; bool need_patch; };
+    auto geo = [&](int n) {
+        TileGeo g;
+        int tb = n;
+        g.t2 = tb % p.ntile[2]; tb /= p.ntile[2];
+        g.t1 = tb % p.ntile[1]; tb /= p.ntile[1];
+        g.t0 = tb;
+        g.c0 = (int64_t)g.t0 * p.TO[0] * p.s[0]; g.c1 = (int64_t)g.t1 * p.TO[1] * p.s[1]; g.c2 = (int64_t)g.t2 * p.TO[2] * p.s[2];
+        const int64_t c[3] = {g.c0, g.c1, g.c2};
+        g.need_patch = false;
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+            if (c[a] < p.pf[a] && !p.front_zero[a]) g.need_patch = true;
+            if (c[a] + p.IT[a] > p.pf[a] + p.n[a] && !p.back_zero[a]) g.need_patch = true;
+        }
+        const int64_t cx2_raw = g.c2 - p.pf[2];
+        g.shift2 = (int)(((cx2_raw % kAlign) + kAlign) % kAlign);
+        g.c2_lo = g.c2 - g.shift2;
+        return g;
+    };
+    auto issue = [&](const TileGeo &g, int buf) {      // thread 0 only
+        const uint32_t mb = smem_u32(&mbar[buf]);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // a halo patch may have written this buffer through the generic proxy
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"((uint32_t)(p.tile_elems * (int)sizeof(T))) : "memory");
+        asm volatile(
+            "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+            ::"r"(smem_u32(smem_raw + buf * tile_bytes)), "l"(reinterpret_cast<uint64_t>(&tmap)), "r"((int)(g.c2_lo - p.pf[2])), "r"((int)(g.c1 - p.pf[1])), "r"((int)(g.c0 - p.pf[0])), "r"(mb)
+            : "memory");
+    };
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (tid == 0 && (int)blockIdx.x < ntiles_total) issue(geo(blockIdx.x), 0);
+    __syncthreads();                                    // kernel rows complete
+    int it = 0;
+    for (int n = blockIdx.x; n < ntiles_total; n += gridDim.x, it++) {
+        const int buf = it & 1;
+        const TileGeo g = geo(n);
+        T *tile = reinterpret_cast<T *>(smem_raw + buf * tile_bytes);
+        // the next tile's box into the other buffer (every thread left it at the barrier that ended the previous iteration)
+        if (tid == 0 && n + (int)gridDim.x < ntiles_total) issue(geo(n + gridDim.x), buf ^ 1);
+        if (g.need_patch) {
+            const int64_t c_lo[3] = {g.c0, g.c1, g.c2};
+            for (int e = tid; e < p.IT[0] + p.IT[1] + row_elems; e += kThreads) {
+                const int a = e < p.IT[0] ? 0 : (e < p.IT[0] + p.IT[1] ? 1 : 2);
+                const int i = e - (a == 0 ? 0 : (a == 1 ? p.IT[0] : p.IT[0] + p.IT[1]));
+                const int64_t c = (a == 2 ? g.c2_lo : c_lo[a]) + i;
+                s_map0[e] = (c < 0 || c >= p.P[a]) ? kBeyond : p.map[a][c];
+            }
+            __syncthreads();
+        }
+        {
+            const uint32_t mb = smem_u32(&mbar[buf]), parity = (uint32_t)((it >> 1) & 1);
+            uint32_t done = 0;
+            while (!done) {
+                asm volatile(
+                    "{\n\t.reg .pred p;\n\t"
+                    "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                    "selp.u32 %0, 1, 0, p;\n\t}"
+                    : "=r"(done) : "r"(mb), "r"(parity) : "memory");
+            }
+        }
+        if (g.need_patch) {
+            auto resolve = [&](int i0, int i1, int i2) -> T {
+                const int32_t m2 = s_map2[i2], m1 = s_map1[i1], m0 = s_map0[i0];
+                if (m2 == kBeyond || m1 == kBeyond || m0 == kBeyond) return Elem<T>::zero();
+                if (m2 == NDC_MAP_CONST_FRONT) return *(const T *)p.cfront[2];
+                if (m2 == NDC_MAP_CONST_BACK) return *(const T *)p.cback[2];
+                if (m1 == NDC_MAP_CONST_FRONT) return *(const T *)p.cfront[1];
+                if (m1 == NDC_MAP_CONST_BACK) return *(const T *)p.cback[1];
+                if (m0 == NDC_MAP_CONST_FRONT) return *(const T *)p.cfront[0];
+                if (m0 == NDC_MAP_CONST_BACK) return *(const T *)p.cback[0];
+                if (m2 == NDC_MAP_INIT || m1 == NDC_MAP_INIT || m0 == NDC_MAP_INIT) return Elem<T>::zero();
+                return ((const T *)p.x)[(int64_t)m0 * p.xstr[0] + (int64_t)m1 * p.xstr[1] + (int64_t)m2 * p.xstr[2]];
+            };
+            auto fill_rows = [&](int nq, int width, int nsel, auto rowmap, auto colmap) {
+                if (nq <= 0 || width <= 0 || nsel <= 0) return;
+                int lanes = 1;
+                while (lanes < nsel && lanes < kThreads) lanes <<= 1;
+                const int rows_it = kThreads / lanes, sub = tid / lanes, ln = tid - sub * lanes;
+                const int total = nq * width;
+                int q = sub / width, j = sub - q * width;
+#pragma unroll 4
+                for (int r = sub; r < total; r += rows_it) {
+                    int i0, i1;
+                    rowmap(q, j, i0, i1);
+                    for (int h = ln; h < nsel; h += lanes) {
+                        const int i2 = colmap(h);
+                        tile[(i0 * p.IT[1] + i1) * row_elems + i2] = resolve(i0, i1, i2);
+                    }
+                    j += rows_it;
+                    while (j >= width) { j -= width; q++; }
+                }
+            };
+            auto ident_col = [&](int h) { return h; };
+            const int lo0 = (int)min((int64_t)p.IT[0], max((int64_t)0, p.pf[0] - g.c0)), hi0 = (int)max((int64_t)lo0, min((int64_t)p.IT[0], p.pf[0] + p.n[0] - g.c0));
+            const int lo1 = (int)min((int64_t)p.IT[1], max((int64_t)0, p.pf[1] - g.c1)), hi1 = (int)max((int64_t)lo1, min((int64_t)p.IT[1], p.pf[1] + p.n[1] - g.c1));
+            const int f2 = (int)min((int64_t)row_elems, max((int64_t)0, p.pf[2] - g.c2_lo));
+            const int b2 = (int)max((int64_t)f2, min((int64_t)row_elems, max((int64_t)0, p.pf[2] + p.n[2] - g.c2_lo)));
+            const int wside = lo1 + (p.IT[1] - hi1);
+            fill_rows(lo0, p.IT[1], row_elems, [&](int q, int j, int &i0, int &i1) { i0 = q; i1 = j; }, ident_col);
+            fill_rows(p.IT[0] - hi0, p.IT[1], row_elems, [&](int q, int j, int &i0, int &i1) { i0 = hi0 + q; i1 = j; }, ident_col);
+            fill_rows(hi0 - lo0, wside, row_elems, [&](int q, int j, int &i0, int &i1) { i0 = lo0 + q; i1 = j < lo1 ? j : hi1 + (j - lo1); }, ident_col);
+            fill_rows(hi0 - lo0, hi1 - lo1, f2 + (row_elems - b2), [&](int q, int j, int &i0, int &i1) { i0 = lo0 + q; i1 = lo1 + j; },
+                      [&](int h) { return h < f2 ? h : b2 + (h - f2); });
+            __syncthreads();
+        }
+        // compute: thread -> (o1, four neighbouring o2) of the tile, TO0 x 4 accumulators in registers
+        {
+            const int T2 = p.TO[2] / kBlockR;
+            const int o2l = (tid % T2) * kBlockR, o1l = tid / T2;
+            if (o1l < p.TO[1]) {
+                const int64_t o1 = (int64_t)g.t1 * p.TO[1] + o1l, o2 = (int64_t)g.t2 * p.TO[2] + o2l;
+                T acc[kMaxTO0][kBlockR];
+                const int base = o1l * (int)p.s[1] * row_elems + o2l * S2;
+                const uint32_t tile_addr16 = smem_u32(tile) + (uint32_t)base * (uint32_t)sizeof(T);
+                const int step0_bytes = (int)p.s[0] * plane_elems * (int)sizeof(T);
+                switch (p.TO[0]) {
+                case 1: blocked_loop_shift<T, 1, S2, D2>(g.shift2, tile_addr16, s_rw, s_roff, s_rmask, p.nrow, p.kk[2], step0_bytes, acc); break;
+                case 2: blocked_loop_shift<T, 2, S2, D2>(g.shift2, tile_addr16, s_rw, s_roff, s_rmask, p.nrow, p.kk[2], step0_bytes, acc); break;
+                default: blocked_loop_shift<T, 4, S2, D2>(g.shift2, tile_addr16, s_rw, s_roff, s_rmask, p.nrow, p.kk[2], step0_bytes, acc); break;
+                }
+                if (o1 < p.O[1]) {
+                    T *out = (T *)p.out;
+#pragma unroll
+                    for (int q = 0; q < kMaxTO0; q++) {
+                        const int64_t o0 = (int64_t)g.t0 * p.TO[0] + q;
+                        if (q < p.TO[0] && o0 < p.O[0]) {
+                            T *orow = out + o0 * p.ostr[0] + o1 * p.ostr[1] + o2;
+#pragma unroll
+                            for (int j = 0; j < kBlockR; j++) if (o2 + j < p.O[2]) orow[j] = acc[q][j];
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();                                // this buffer (and the window maps) may be overwritten from the next iteration on
     }
 }
 

@@ -61,14 +61,27 @@ print("RESULT", "ok" if bad == 0 else "bad")
 """
 
 
-@pytest.mark.gpu
-def test_blocked_direct_conv_bit_exact(pkg, cuda_lib):
-    e = dict(os.environ); e["NDCONV_BLOCKED_MIN_OUT"] = "0"; e["NDCONV_DEBUG_BLOCKED"] = "1"
+def _child(env):
+    e = dict(os.environ); e.update(env)
     r = subprocess.run([sys.executable, "-c", _CHILD.format(root=str(ROOT))], capture_output=True, text=True, env=e, timeout=1500)
     assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-3000:])
     assert "RESULT ok" in r.stdout, r.stdout[-3000:]
+    return r
+
+
+@pytest.mark.gpu
+def test_blocked_direct_conv_bit_exact(pkg, cuda_lib):
+    r = _child({"NDCONV_BLOCKED_MIN_OUT": "0", "NDCONV_DEBUG_BLOCKED": "1", "NDCONV_DISABLE_PERSIST": "1"})
     # the variant really ran (the library reports each blocked launch on stderr under NDCONV_DEBUG_BLOCKED)
     assert r.stderr.count("[ndconv] blocked direct conv") >= len(CASES) - 2, r.stderr[-2000:]
+
+
+@pytest.mark.gpu
+def test_persistent_direct_conv_bit_exact(pkg, cuda_lib):
+    """the persistent double-buffered variant (large problems only by default): forced onto the small cases with THREE CTAs, so that every
+    CTA walks several tiles through both window buffers, interior and edge tiles (halo patch) alike"""
+    r = _child({"NDCONV_BLOCKED_MIN_OUT": "0", "NDCONV_DEBUG_BLOCKED": "1", "NDCONV_PERSIST_MIN_TILES": "0", "NDCONV_PERSIST_MAX_GRID": "3"})
+    assert r.stderr.count("[ndconv] persistent direct conv") >= 6, r.stderr[-2000:]      # the cases whose two windows fit one CTA
 
 
 def test_blocked_cases_are_well_formed():
