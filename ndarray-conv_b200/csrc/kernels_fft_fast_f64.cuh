@@ -157,8 +157,9 @@ __global__ void __launch_bounds__(128, 4) row_fwd_d(const __grid_constant__ RowP
     for (; wi < nwarp_items; wi += wstep) {
         const RowSrcInfoD ri = nxt;
         if (wi + wstep < nwarp_items) nxt = resolve_fwd_row_d<N>(p, (wi + wstep) * G + g, L + kPadD);
-        if (__all_sync(0xffffffffu, !ri.active || ri.beyond)) {
-            // rows beyond the padded extent of an outer axis: zero spectrum, no transform
+        if (__all_sync(0xffffffffu, !ri.active || ri.beyond || ((ri.has_const ? ri.cval == 0.0 : ri.zero) && p.cfront[al] == 0.0 && p.cback[al] == 0.0))) {
+            // rows beyond the padded extent of an outer axis, and all-zero rows (a Zeros border or a never-written plane of an outer axis, no
+            // non-zero constant border on the last axis): zero spectrum, no transform
             if (ri.active) for (int q = t; q < L + kPadD; q += T) st_cd(ri.dst + q, cd{0.0, 0.0});
             continue;
         }
@@ -168,6 +169,33 @@ __global__ void __launch_bounds__(128, 4) row_fwd_d(const __grid_constant__ RowP
             const double *rowp = p.x + ri.base - p.pf[al];                // padded column cl of this row is rowp[cl] where it is an array sample
             const int64_t lo = p.pf[al], hi = p.pf[al] + p.n[al];
             const int flags = (ri.active ? 1 : 0) | (ri.beyond ? 2 : 0) | (ri.zero ? 4 : 0) | (ri.has_const ? 8 : 0);
+            if (!plain && p.xstr[al] == 1) {
+                // a row without array samples (an outer axis sits in a Zeros / Const border or a never-written plane): its value depends on
+                // the column only through the last axis' own constant borders -- no loads from x, map lookups in the border columns only, no calls (these are most
+                // rows of a small padded problem: every pair of them through border_pair cost c3 12 us)
+                const double rowval = ri.has_const ? ri.cval : 0.0;
+                const bool live = ri.active && !ri.beyond;
+#pragma unroll
+                for (int j = 0; j < R1; j++) {
+                    const int64_t cl = ri.cl0 + 2 * (t + T * j);
+                    double q[2];
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        const int64_t c1 = cl + h;
+                        double val = 0.0;
+                        if (live && c1 < p.P[al]) {
+                            val = rowval;
+                            if (c1 < lo || c1 >= hi) {                 // the last axis' own border: a constant fill there wins
+                                const int32_t m = p.map[al][c1];
+                                if (m == NDC_MAP_CONST_FRONT) val = p.cfront[al];
+                                else if (m == NDC_MAP_CONST_BACK) val = p.cback[al];
+                            }
+                        }
+                        q[h] = val;
+                    }
+                    v[j] = cd{q[0], q[1]};
+                }
+            } else
 #pragma unroll
             for (int j = 0; j < R1; j++) {
                 const int64_t cl = ri.cl0 + 2 * (t + T * j);
