@@ -215,6 +215,15 @@ __global__ void __launch_bounds__(128, 4) row_fwd_d(const __grid_constant__ RowP
 #pragma unroll
             for (int i = 0; i < T; i++) v[m * T + i] = ld_cd(sb + (t + T * m) * (T + 1) + i);
         __syncwarp();
+        // the next row's samples are requested into L2 now (after this row's exchange, as in fast::row_fwd): 4 L reals = 32 T doubles per row,
+        // one 128-byte line per lane and half
+        if (wi + wstep < nwarp_items && nxt.active && !nxt.beyond && !nxt.zero && !nxt.has_const && p.xstr[al] == 1) {
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int64_t cc = nxt.cl0 - p.pf[al] + 16 * (t + T * h);
+                if (cc >= 0 && cc < p.n[al]) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.x + nxt.base + cc));
+            }
+        }
 #pragma unroll
         for (int m = 0; m < M; m++) dftd<false, T>(v + m * T);            // v[m*T + k2] = Z[k], k = t + T m + 16 k2
         // partner Z[L-k] and R2C post-processing; primaries are k2 < T/2 (k < L/2):
