@@ -12,7 +12,11 @@ from test_parity_small import fft_tol, mode_from_spec, padding_from_spec
 
 CASES = [((1000, 20, 300), (3, 3, 3), 1, "full", ("custom", ["replicate", "circular", "zeros"]), False),
          ((3, 1000, 300), (2, 3, 5), 1, "same", "reflect", True),
-         ((1300, 2600), (5, 9), 1, "full", "reflect", True)]
+         ((1300, 2600), (5, 9), 1, "full", "reflect", True),
+         # round 2b: the Tensor-Memory-resident column pass (>= 10 tiles of 1024 rows): few chunks per CTA / one bundle / the c5 tile shape
+         ((10200, 520), (3, 9), 1, "same", ("const", 0.5), True),
+         ((12000, 1000), (5, 5), 1, "same", ("custom", ["replicate", "circular"]), False),
+         ((4000, 6500), (9, 5), 1, "full", "reflect", True)]
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 12
 bad = 0
 for shape, ks, dil, mode, padding, rev in CASES:
