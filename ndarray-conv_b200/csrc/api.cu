@@ -404,11 +404,9 @@ static int launch_direct_persistent_sd(ndconv_processor *p, const CUtensorMap &t
 template <class T>
 static int launch_direct_persistent(ndconv_processor *p, const CUtensorMap &tm, const tile::TileParams &tp, int64_t ntiles, size_t smem, double alg_bytes)
 {
-    const int s2 = (int)tp.s[2], d2 = tp.dd[2];
-    if (s2 == 1 && d2 == 1) return launch_direct_persistent_sd<T, 1, 1>(p, tm, tp, ntiles, smem, alg_bytes);
-    if (s2 == 2 && d2 == 1) return launch_direct_persistent_sd<T, 2, 1>(p, tm, tp, ntiles, smem, alg_bytes);
-    if (s2 == 1 && d2 == 2) return launch_direct_persistent_sd<T, 1, 2>(p, tm, tp, ntiles, smem, alg_bytes);
-    return launch_direct_persistent_sd<T, 2, 2>(p, tm, tp, ntiles, smem, alg_bytes);
+    // (stride 1 only: the instantiations for stride 2 would double the compile time of the tile kernels for a case nothing measured needs)
+    if (tp.dd[2] == 1) return launch_direct_persistent_sd<T, 1, 1>(p, tm, tp, ntiles, smem, alg_bytes);
+    return launch_direct_persistent_sd<T, 1, 2>(p, tm, tp, ntiles, smem, alg_bytes);
 }
 
 // returns NDCONV_OK with *used = false when the problem is outside the tile kernel's envelope (caller falls back)
@@ -529,7 +527,7 @@ static int try_direct_tile(ndconv_processor *p, const ndconv_problem *pr, const 
     // measured (profiles/r02d_*): two window buffers per CTA win on rank-2 problems (8192^2 k = 7x7 f32 666 -> 616 us, 4096^2 k = 5x5 dilation 2 f64
     // 281 -> 210 us) and lose 5-13 % on rank 3, where the TMA boxes of 4 output planes re-read 6 input planes and box traffic, not latency, is the
     // bound; the tests force it onto rank 3 as well (NDCONV_PERSIST_MIN_TILES=0)
-    const bool persist_rank = persist_min_tiles >= 0 || tp.n[0] == 1;
+    const bool persist_rank = (persist_min_tiles >= 0 || tp.n[0] == 1) && tp.s[2] == 1;
     if (use_blocked && tma && !no_persist && persist_rank && 2 * tile_bytes + tap_bytes + 256 <= 100 * 1024 && grid >= (persist_min_tiles >= 0 ? persist_min_tiles : 4 * (int64_t)p->num_sms)) {
         const size_t smem2 = 2 * tile_bytes + tap_bytes + 128;
         switch (g.dtype) {

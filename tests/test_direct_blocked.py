@@ -81,7 +81,7 @@ def test_persistent_direct_conv_bit_exact(pkg, cuda_lib):
     """the persistent double-buffered variant (large problems only by default): forced onto the small cases with THREE CTAs, so that every
     CTA walks several tiles through both window buffers, interior and edge tiles (halo patch) alike"""
     r = _child({"NDCONV_BLOCKED_MIN_OUT": "0", "NDCONV_DEBUG_BLOCKED": "1", "NDCONV_PERSIST_MIN_TILES": "0", "NDCONV_PERSIST_MAX_GRID": "3"})
-    assert r.stderr.count("[ndconv] persistent direct conv") >= 6, r.stderr[-2000:]      # the cases whose two windows fit one CTA
+    assert r.stderr.count("[ndconv] persistent direct conv") >= 3, r.stderr[-2000:]      # the stride-1 cases whose two windows fit one CTA
 
 
 def test_blocked_cases_are_well_formed():
