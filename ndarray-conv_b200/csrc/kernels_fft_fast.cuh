@@ -37,6 +37,16 @@ namespace fast {
 DEV void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
 DEV void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+// Experiments only (tools/exp/ring_bound.sh builds a second library with -DNDCONV_EXP_RING): every tile's spectra land in slot
+// tile % ring of the workspace, so the workspace traffic of each pass stays in L2 -- RESULTS ARE GARBAGE; the timings bound what a
+// fused, L2-resident pipeline could reach.  The product library is built without the macro.
+#ifdef NDCONV_EXP_RING
+__device__ int g_exp_ring = 1 << 30;
+#define NDC_RING_TILE(t) ((t) % g_exp_ring)
+#else
+#define NDC_RING_TILE(t) (t)
+#endif
+
 typedef cx<float> cf;
 typedef pk::pcf pc;              // the same 8 bytes as cf, held as one 64-bit register pair for FADD2 / FMUL2 / FFMA2 (packed_cf.cuh)
 constexpr int kPad = 8;          // extra columns per row: Nyquist + 7 zeros (keeps rows 64-byte aligned; 128-byte rows measured no faster)
@@ -109,7 +119,7 @@ template <int N> __device__ __forceinline__ RowSrcInfo resolve_fwd_row(const Row
     const uint32_t w32 = (uint32_t)w, rpt = (uint32_t)p.rows_per_tile;
     const uint32_t tile = w32 / rpt;
     uint32_t row = w32 - tile * rpt;
-    r.dst = p.ws + (int64_t)tile * p.tile_elems + (int64_t)row * pitch;
+    r.dst = p.ws + (int64_t)NDC_RING_TILE(tile) * p.tile_elems + (int64_t)row * pitch;
     uint32_t tt = tile;
     const uint32_t tl = tt % (uint32_t)p.ntiles[N - 1]; tt /= (uint32_t)p.ntiles[N - 1];
     r.cl0 = (int64_t)tl * p.V[N - 1];
@@ -348,7 +358,7 @@ template <int N> __device__ __forceinline__ RowInvInfo resolve_inv_row(const Row
         obase = obase * p.O[a] + o[a];
     }
     tile = tile * ntl + r.tl;
-    r.src = p.ws + tile * p.tile_elems + row * pitch;
+    r.src = p.ws + NDC_RING_TILE(tile) * p.tile_elems + row * pitch;
     r.orow = obase * p.O[N - 1];
     return r;
 }
@@ -1347,7 +1357,7 @@ col_pass_tma_kres(const __grid_constant__ ColParams p, const __grid_constant__ C
 #pragma unroll
         for (int b = 0; b < F / C::box_rows; b++)
             asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-                         ::"r"(sP + b * C::box_rows * 64), "l"(reinterpret_cast<uint64_t>(&tm_ld)), "r"((int)(ib * 8)), "r"((int)(t * F + b * C::box_rows)), "r"(mb)
+                         ::"r"(sP + b * C::box_rows * 64), "l"(reinterpret_cast<uint64_t>(&tm_ld)), "r"((int)(ib * 8)), "r"((int)(NDC_RING_TILE(t) * F + b * C::box_rows)), "r"(mb)
                          : "memory");
     };
     pdl_wait();                                      // before the first access to the workspace (and to kres, which an earlier kernel of the stream wrote)
@@ -1438,7 +1448,7 @@ col_pass_tma_kres(const __grid_constant__ ColParams p, const __grid_constant__ C
             for (int b = 0; b < nst; b++) {
                 const int r = p.skip + b * p.store_rows;
                 asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
-                             ::"l"(reinterpret_cast<uint64_t>(&tm_st)), "r"((int)(ib * 8)), "r"((int)(t * F + r)), "r"(sX + r * 64) : "memory");
+                             ::"l"(reinterpret_cast<uint64_t>(&tm_st)), "r"((int)(ib * 8)), "r"((int)(NDC_RING_TILE(t) * F + r)), "r"(sX + r * 64) : "memory");
             }
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
