@@ -258,7 +258,9 @@ def run_gpu(args, w, rank, world, local_rank):
 
     # ---- slab of this rank (overlap-save along axis 0) ----
     pads, strides = mode.unfold(kshape, [dil] * 2, lib)
-    sl = pkg.slab_plan((n0, n1), np.float32, kwd, mode, pmode, pkg.PATH_FFT, world, rank, lib)
+    # --as-slab W:R (kernel experiments on one GPU): time the slab rank R of a W-rank run would get; the line is NOT a bench value
+    plan_world, plan_rank = (int(args.as_slab.split(":")[0]), int(args.as_slab.split(":")[1])) if args.as_slab else (world, rank)
+    sl = pkg.slab_plan((n0, n1), np.float32, kwd, mode, pmode, pkg.PATH_FFT, plan_world, plan_rank, lib)
     Kd0 = (kshape[0] - 1) * dil + 1
     pf0, pb0 = int(pads[0][0]), int(pads[0][1])
     pb_, pe_ = sl["pad_begin"], sl["pad_end"]              # rows of the padded axis 0 this rank reads
@@ -432,6 +434,8 @@ def run_gpu(args, w, rank, world, local_rank):
             "assembled_check": assembled,
             "workspace_bytes": proc.workspace_bytes,
         }
+        if args.as_slab:
+            line["invalid_as_slab"] = args.as_slab       # a kernel experiment: one slab of a larger run, not a bench value
         if shapes is not None:
             line["other_shapes"] = shapes
         if cpu_v is not None:
@@ -665,6 +669,7 @@ def main():
     ap.add_argument("--no-shapes", action="store_true", help="skip the secondary per-shape numbers (configs c1-c4)")
     ap.add_argument("--no-verify", action="store_true", help="N > 1: skip the comparison of the assembled N-rank output with rank 0's one-GPU answer")
     ap.add_argument("--gpu-pick", default="spread", choices=["spread", "linear"], help="N ranks on a box with more GPUs: spread them over the GPU indices (default) or take GPUs 0 .. N-1")
+    ap.add_argument("--as-slab", default="", help="W:R -- one GPU times the slab of rank R of W (per-kernel study of the N-GPU case; implies an invalid bench line)")
     ap.add_argument("--ref-sample", action="store_true", help="reference arm: force the bounded row-slab sample instead of the full workload")
     ap.add_argument("--ref-budget-s", type=float, default=150.0, help="reference arm: wall-clock budget for its repetitions (at least one timed step is always run)")
     args = ap.parse_args()

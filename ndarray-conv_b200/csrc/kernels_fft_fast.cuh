@@ -72,6 +72,23 @@ __device__ __forceinline__ pc ld_pc_keep(const cf *p, uint64_t pol)
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
+// dst[k * dst_stride] = v[k] * tw[k * tw_stride] (CONJ: times the conjugate), k < N, both in shared memory.  The twiddles are fetched B at a
+// time BEFORE the stores that follow them: the compiler cannot move a shared-memory load above a shared-memory store it cannot
+// disambiguate, and one LDS -> multiply -> STS chain per k left every twiddle's load latency exposed (ncu source page of c5, round 2e:
+// the first consumer of each twiddle held 12 % of row_fwd's and 10 % of row_inv's stall samples).
+template <int N, bool CONJ, int B = 8>
+__device__ __forceinline__ void twiddle_store(const pc *v, const pc *tw, int tw_stride, pc *dst, int dst_stride)
+{
+#pragma unroll
+    for (int k0 = 0; k0 < N; k0 += B) {
+        pc w[B];
+#pragma unroll
+        for (int e = 0; e < B; e++) if (k0 + e < N) w[e] = tw[(k0 + e) * tw_stride];
+#pragma unroll
+        for (int e = 0; e < B; e++) if (k0 + e < N) dst[(k0 + e) * dst_stride] = CONJ ? pk::cmulc(v[k0 + e], w[e]) : pk::cmul(v[k0 + e], w[e]);
+    }
+}
+
 struct RowParams {
     int ndim;                                  // 2 or 3
     int64_t n[3], xstr[3], P[3], pf[3];
@@ -285,8 +302,7 @@ __global__ void __launch_bounds__(128, 4) row_fwd(const __grid_constant__ RowPar
             }
         }
         pk::dft<false, 32>(v);                                           // over j -> k1
-#pragma unroll
-        for (int k1 = 0; k1 < 32; k1++) sb[k1 * (T + 1) + t] = pk::cmul(v[k1], s_tw[k1 * T + t]);
+        twiddle_store<32, false>(v, s_tw + t, T, sb + t, T + 1);
         __syncwarp();
 #pragma unroll
         for (int m = 0; m < M; m++)
@@ -445,9 +461,7 @@ __global__ void __launch_bounds__(128, 4) row_inv(const __grid_constant__ RowPar
 #pragma unroll
         for (int m = 0; m < M; m++) pk::dft<true, T>(v + m * T);
 #pragma unroll
-        for (int m = 0; m < M; m++)
-#pragma unroll
-            for (int i = 0; i < T; i++) sb[(t + T * m) * (T + 1) + i] = pk::cmulc(v[m * T + i], s_tw[i * 32 + (t + T * m)]);
+        for (int m = 0; m < M; m++) twiddle_store<T, true>(v + m * T, s_tw + (t + T * m), 32, sb + (t + T * m) * (T + 1), 1);
         __syncwarp();
 #pragma unroll
         for (int k1 = 0; k1 < 32; k1++) v[k1] = sb[k1 * (T + 1) + t];
@@ -459,18 +473,25 @@ __global__ void __launch_bounds__(128, 4) row_inv(const __grid_constant__ RowPar
         const int Kd1 = p.Kd[al];
         const int64_t mbase = (int64_t)cur.tl * p.V[al];
         if (p.s[al] == 1) {
-            const int64_t obase = cur.orow + mbase - (Kd1 - 1);
-            const bool vec_ok = (obase & 1) == 0;
+            // Tile samples [lo, hi) are output elements outp[i].  This lane holds samples i0 + 2T j (+ 1): the kept ones are the j of one
+            // interval per half, worked out once in 32-bit arithmetic, so a store costs two compares against constants and an immediate
+            // offset (the per-store 64-bit index arithmetic and bound checks were ~30 % of this kernel's executed instructions).
+            float *outp = p.out + (cur.orow + mbase - (Kd1 - 1));
+            const int64_t room = p.O[al] - (mbase - (Kd1 - 1));
+            const int lo = Kd1 - 1, hi = room < (int64_t)(2 * L) ? (int)room : 2 * L;
+            const int i0 = 2 * t;
+            constexpr int SH = T == 32 ? 6 : T == 16 ? 5 : T == 8 ? 4 : 3;                   // log2(2 T); (x + 2T - 1) >> SH = ceil(x / 2T) for any sign
+            const int ja0 = (lo - i0 + 2 * T - 1) >> SH, jb0 = (hi - i0 + 2 * T - 1) >> SH;   // sample i0 + 2T j is kept for j in [ja0, jb0)
+            const int ja1 = (lo - i0 + 2 * T - 2) >> SH, jb1 = (hi - i0 + 2 * T - 2) >> SH;   // sample i0 + 1 + 2T j for j in [ja1, jb1)
+            const bool vec_ok = (reinterpret_cast<uintptr_t>(outp) & 7) == 0;
+            float *o = outp + i0;
 #pragma unroll
             for (int j = 0; j < 32; j++) {
-                const int i = 2 * (t + T * j);
-                const int64_t o_lo = mbase + i - (Kd1 - 1);
-                const bool ok0 = i >= Kd1 - 1 && o_lo < p.O[al];
-                const bool ok1 = i + 1 >= Kd1 - 1 && o_lo + 1 < p.O[al];
-                if (vec_ok && ok0 && ok1) *reinterpret_cast<unsigned long long *>(p.out + cur.orow + o_lo) = v[j].v;
+                const bool ok0 = j >= ja0 && j < jb0, ok1 = j >= ja1 && j < jb1;
+                if (vec_ok && ok0 && ok1) *reinterpret_cast<unsigned long long *>(o + 2 * T * j) = v[j].v;
                 else {
-                    if (ok0) p.out[cur.orow + o_lo] = pk::re(v[j]);
-                    if (ok1) p.out[cur.orow + o_lo + 1] = pk::im(v[j]);
+                    if (ok0) o[2 * T * j] = pk::re(v[j]);
+                    if (ok1) o[2 * T * j + 1] = pk::im(v[j]);
                 }
             }
         } else {
@@ -545,8 +566,7 @@ __global__ void __launch_bounds__(128, 4) row_fwd_c(const __grid_constant__ RowP
             }
         }
         pk::dft<false, 32>(v);
-#pragma unroll
-        for (int k1 = 0; k1 < 32; k1++) sb[k1 * (T + 1) + t] = pk::cmul(v[k1], s_tw[k1 * T + t]);
+        twiddle_store<32, false>(v, s_tw + t, T, sb + t, T + 1);
         __syncwarp();
 #pragma unroll
         for (int m = 0; m < M; m++)
@@ -591,9 +611,7 @@ __global__ void __launch_bounds__(128, 4) row_inv_c(const __grid_constant__ RowP
 #pragma unroll
         for (int m = 0; m < M; m++) pk::dft<true, T>(v + m * T);
 #pragma unroll
-        for (int m = 0; m < M; m++)
-#pragma unroll
-            for (int i = 0; i < T; i++) sb[(t + T * m) * (T + 1) + i] = pk::cmulc(v[m * T + i], s_tw[i * 32 + (t + T * m)]);
+        for (int m = 0; m < M; m++) twiddle_store<T, true>(v + m * T, s_tw + (t + T * m), 32, sb + (t + T * m) * (T + 1), 1);
         __syncwarp();
 #pragma unroll
         for (int k1 = 0; k1 < 32; k1++) v[k1] = sb[k1 * (T + 1) + t];
@@ -696,8 +714,7 @@ __global__ void __launch_bounds__(128, 3) row1d(const __grid_constant__ RowParam
         }
         // ---- forward: radix 32 over j, twiddle, exchange, radix T ----
         pk::dft<false, 32>(v);
-#pragma unroll
-        for (int k1 = 0; k1 < 32; k1++) sb[k1 * (T + 1) + t] = pk::cmul(v[k1], s_twF[k1 * T + t]);
+        twiddle_store<32, false>(v, s_twF + t, T, sb + t, T + 1);
         __syncwarp();
 #pragma unroll
         for (int m = 0; m < M; m++)
@@ -764,8 +781,7 @@ __global__ void __launch_bounds__(128, 3) row1d(const __grid_constant__ RowParam
         __syncwarp();
 #pragma unroll
         for (int m = 0; m < M; m++)
-#pragma unroll
-            for (int i = 0; i < T; i++) sb[(t + T * m) * (T + 1) + i] = pk::cmulc(v[m * T + i], s_twI[i * 32 + (t + T * m)]);
+            twiddle_store<T, true>(v + m * T, s_twI + (t + T * m), 32, sb + (t + T * m) * (T + 1), 1);
         __syncwarp();
 #pragma unroll
         for (int k1 = 0; k1 < 32; k1++) v[k1] = sb[k1 * (T + 1) + t];
@@ -860,8 +876,7 @@ __global__ void __launch_bounds__(128, 4) row1d_c(const __grid_constant__ RowPar
             }
         }
         pk::dft<false, 32>(v);
-#pragma unroll
-        for (int k1 = 0; k1 < 32; k1++) sb[k1 * (T + 1) + t] = pk::cmul(v[k1], s_twF[k1 * T + t]);
+        twiddle_store<32, false>(v, s_twF + t, T, sb + t, T + 1);
         __syncwarp();
 #pragma unroll
         for (int m = 0; m < M; m++)
@@ -878,8 +893,7 @@ __global__ void __launch_bounds__(128, 4) row1d_c(const __grid_constant__ RowPar
         for (int m = 0; m < M; m++) pk::dft<true, T>(v + m * T);
 #pragma unroll
         for (int m = 0; m < M; m++)
-#pragma unroll
-            for (int i = 0; i < T; i++) sb[(t + T * m) * (T + 1) + i] = pk::cmulc(v[m * T + i], s_twI[i * 32 + (t + T * m)]);
+            twiddle_store<T, true>(v + m * T, s_twI + (t + T * m), 32, sb + (t + T * m) * (T + 1), 1);
         __syncwarp();
 #pragma unroll
         for (int k1 = 0; k1 < 32; k1++) v[k1] = sb[k1 * (T + 1) + t];
@@ -978,8 +992,7 @@ __global__ void __launch_bounds__(ColCfg<E, Tc>::threads, ColCfg<E, Tc>::min_blo
             for (int j = 0; j < E; j++) v[j] = S[(i + Tc * j) * 8 + c];
             __syncthreads();
             pk::dft<false, E>(v);
-#pragma unroll
-            for (int k1 = 0; k1 < E; k1++) S[k1 * pitch + i * 8 + c] = pk::cmul(v[k1], s_tw[k1 * Tc + i]);
+            twiddle_store<E, false>(v, s_tw + i, Tc, S + i * 8 + c, pitch);
             __syncthreads();
 #pragma unroll
             for (int m = 0; m < Mc; m++)
@@ -1014,8 +1027,7 @@ __global__ void __launch_bounds__(ColCfg<E, Tc>::threads, ColCfg<E, Tc>::min_blo
             // so the inverse is the forward flow with conjugated twiddles (no transposed table needed)
             pk::dft<true, E>(v);
             __syncthreads();                               // every thread has finished reading S
-#pragma unroll
-            for (int n1 = 0; n1 < E; n1++) S[n1 * pitch + i * 8 + c] = pk::cmulc(v[n1], s_tw[n1 * Tc + i]);
+            twiddle_store<E, true>(v, s_tw + i, Tc, S + i * 8 + c, pitch);
             __syncthreads();
 #pragma unroll
             for (int ii = 0; ii < Tc; ii++) v[ii] = S[i * pitch + ii * 8 + c];
@@ -1027,8 +1039,7 @@ __global__ void __launch_bounds__(ColCfg<E, Tc>::threads, ColCfg<E, Tc>::min_blo
             __syncthreads();                               // every thread has finished reading S
 #pragma unroll
             for (int m = 0; m < Mc; m++)
-#pragma unroll
-                for (int ii = 0; ii < Tc; ii++) S[(i + Tc * m) * pitch + ii * 8 + c] = pk::cmulc(v[m * Tc + ii], s_twT[ii * E + (i + Tc * m)]);
+                twiddle_store<Tc, true>(v + m * Tc, s_twT + (i + Tc * m), E, S + (i + Tc * m) * pitch + c, 8);
             __syncthreads();
             // after the exchange thread i owns "time" index i of every k1 row
 #pragma unroll

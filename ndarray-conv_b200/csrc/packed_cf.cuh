@@ -31,8 +31,11 @@ __device__ __forceinline__ pcf neg(pcf a) { return mk(-re(a), -im(a)); }
 // a * (-i) (forward) / a * (+i) (inverse)
 template <bool INV> __device__ __forceinline__ pcf mul_neg_i(pcf a) { return INV ? mk(-im(a), re(a)) : mk(im(a), -re(a)); }
 __device__ __forceinline__ pcf scale(pcf a, float s) { return mul(a, mk(s, s)); }
-// a * w
-__device__ __forceinline__ pcf cmul(pcf a, float wre, float wim) { return fma(swap(a), mk(-wim, wim), mul(a, mk(wre, wre))); }
+// a * w = (a.re, a.im) * wre + (-a.im, a.re) * wim.  Written with the sign on the swapped COPY OF a (not on the twiddle): ptxas folds
+// the swap and the half-negation into the FFMA2 operand (`-R.F32x2.LO_HI.NP`) and broadcasts wim as a scalar, so a multiply by a
+// run-time twiddle is exactly FMUL2 + FFMA2.  The earlier form fma(swap(a), (-wim, wim), ...) cost an FADD and a MOV per twiddle to
+// build the (-wim, wim) pair -- and made them the first consumers of the twiddle's LDS.  Same roundings, bit-identical results.
+__device__ __forceinline__ pcf cmul(pcf a, float wre, float wim) { return fma(mk(-im(a), re(a)), mk(wim, wim), mul(a, mk(wre, wre))); }
 __device__ __forceinline__ pcf cmul(pcf a, pcf w) { return cmul(a, re(w), im(w)); }
 // a * conj(w)
 __device__ __forceinline__ pcf cmulc(pcf a, pcf w) { return cmul(a, re(w), -im(w)); }
