@@ -42,9 +42,12 @@ DEV void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 // fused, L2-resident pipeline could reach.  The product library is built without the macro.
 #ifdef NDCONV_EXP_RING
 __device__ int g_exp_ring = 1 << 30;
+__device__ int g_exp_flags = 0;            // col_pass_tma_kres: 1 = no workspace loads (compute on what the landing buffer holds), 2 = no stores
 #define NDC_RING_TILE(t) ((t) % g_exp_ring)
+#define NDC_EXP_FLAG(b) ((g_exp_flags & (b)) != 0)
 #else
 #define NDC_RING_TILE(t) (t)
+#define NDC_EXP_FLAG(b) false
 #endif
 
 typedef cx<float> cf;
@@ -71,6 +74,22 @@ __device__ __forceinline__ pc ld_pc_keep(const cf *p, uint64_t pol)
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// Crop of a tile row at the store: tile samples [lo, hi) are output elements.  A lane holds samples i0 + STEP j and i0 + 1 + STEP j
+// (STEP = 2 T, a power of two); the kept ones are the j of one interval per half -- [ja0, jb0) and [ja1, jb1) -- worked out once in 32-bit
+// arithmetic, so a store costs two compares against constants and an immediate offset (the per-store 64-bit index arithmetic and bound
+// checks were ~30 % of row_inv's executed instructions on c5).
+struct KeepRange { int ja0, jb0, ja1, jb1; };
+template <int STEP> __device__ __forceinline__ KeepRange keep_range(int lo, int hi, int i0)
+{
+    static_assert(STEP > 0 && (STEP & (STEP - 1)) == 0, "power of two");
+    constexpr int SH = STEP == 128 ? 7 : STEP == 64 ? 6 : STEP == 32 ? 5 : STEP == 16 ? 4 : STEP == 8 ? 3 : STEP == 4 ? 2 : 1;
+    static_assert((1 << SH) == STEP, "2 <= STEP <= 128");
+    KeepRange k;                                                                   // (x + STEP - 1) >> SH = ceil(x / STEP) for either sign
+    k.ja0 = (lo - i0 + STEP - 1) >> SH; k.jb0 = (hi - i0 + STEP - 1) >> SH;
+    k.ja1 = (lo - i0 + STEP - 2) >> SH; k.jb1 = (hi - i0 + STEP - 2) >> SH;
+    return k;
+}
 
 // dst[k * dst_stride] = v[k] * tw[k * tw_stride] (CONJ: times the conjugate), k < N, both in shared memory.  The twiddles are fetched B at a
 // time BEFORE the stores that follow them: the compiler cannot move a shared-memory load above a shared-memory store it cannot
@@ -473,21 +492,15 @@ __global__ void __launch_bounds__(128, 4) row_inv(const __grid_constant__ RowPar
         const int Kd1 = p.Kd[al];
         const int64_t mbase = (int64_t)cur.tl * p.V[al];
         if (p.s[al] == 1) {
-            // Tile samples [lo, hi) are output elements outp[i].  This lane holds samples i0 + 2T j (+ 1): the kept ones are the j of one
-            // interval per half, worked out once in 32-bit arithmetic, so a store costs two compares against constants and an immediate
-            // offset (the per-store 64-bit index arithmetic and bound checks were ~30 % of this kernel's executed instructions).
-            float *outp = p.out + (cur.orow + mbase - (Kd1 - 1));
+            float *outp = p.out + (cur.orow + mbase - (Kd1 - 1));                          // tile sample i -> outp[i]
             const int64_t room = p.O[al] - (mbase - (Kd1 - 1));
-            const int lo = Kd1 - 1, hi = room < (int64_t)(2 * L) ? (int)room : 2 * L;
             const int i0 = 2 * t;
-            constexpr int SH = T == 32 ? 6 : T == 16 ? 5 : T == 8 ? 4 : 3;                   // log2(2 T); (x + 2T - 1) >> SH = ceil(x / 2T) for any sign
-            const int ja0 = (lo - i0 + 2 * T - 1) >> SH, jb0 = (hi - i0 + 2 * T - 1) >> SH;   // sample i0 + 2T j is kept for j in [ja0, jb0)
-            const int ja1 = (lo - i0 + 2 * T - 2) >> SH, jb1 = (hi - i0 + 2 * T - 2) >> SH;   // sample i0 + 1 + 2T j for j in [ja1, jb1)
+            const KeepRange kr = keep_range<2 * T>(Kd1 - 1, room < (int64_t)(2 * L) ? (int)room : 2 * L, i0);
             const bool vec_ok = (reinterpret_cast<uintptr_t>(outp) & 7) == 0;
             float *o = outp + i0;
 #pragma unroll
             for (int j = 0; j < 32; j++) {
-                const bool ok0 = j >= ja0 && j < jb0, ok1 = j >= ja1 && j < jb1;
+                const bool ok0 = j >= kr.ja0 && j < kr.jb0, ok1 = j >= kr.ja1 && j < kr.jb1;
                 if (vec_ok && ok0 && ok1) *reinterpret_cast<unsigned long long *>(o + 2 * T * j) = v[j].v;
                 else {
                     if (ok0) o[2 * T * j] = pk::re(v[j]);
@@ -792,18 +805,19 @@ __global__ void __launch_bounds__(128, 3) row1d(const __grid_constant__ RowParam
         const int Kd1 = p.Kd[0];
         const int64_t mbase = tl * p.V[0];
         if (p.s[0] == 1) {
-            const int64_t obase = mbase - (Kd1 - 1);
-            const bool vec_ok = (obase & 1) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 7) == 0;
+            float *outp = p.out + (mbase - (Kd1 - 1));                                     // tile sample i -> outp[i] (see row_inv)
+            const int64_t room = p.O[0] - (mbase - (Kd1 - 1));
+            const int i0 = 2 * t;
+            const KeepRange kr = keep_range<2 * T>(Kd1 - 1, room < (int64_t)(2 * L) ? (int)room : 2 * L, i0);
+            const bool vec_ok = (reinterpret_cast<uintptr_t>(outp) & 7) == 0;
+            float *o = outp + i0;
 #pragma unroll
             for (int j = 0; j < 32; j++) {
-                const int i = 2 * (t + T * j);
-                const int64_t o_lo = mbase + i - (Kd1 - 1);
-                const bool ok0 = i >= Kd1 - 1 && o_lo < p.O[0];
-                const bool ok1 = i + 1 >= Kd1 - 1 && o_lo + 1 < p.O[0];
-                if (vec_ok && ok0 && ok1) *reinterpret_cast<unsigned long long *>(p.out + o_lo) = v[j].v;
+                const bool ok0 = j >= kr.ja0 && j < kr.jb0, ok1 = j >= kr.ja1 && j < kr.jb1;
+                if (vec_ok && ok0 && ok1) *reinterpret_cast<unsigned long long *>(o + 2 * T * j) = v[j].v;
                 else {
-                    if (ok0) p.out[o_lo] = pk::re(v[j]);
-                    if (ok1) p.out[o_lo + 1] = pk::im(v[j]);
+                    if (ok0) o[2 * T * j] = pk::re(v[j]);
+                    if (ok1) o[2 * T * j + 1] = pk::im(v[j]);
                 }
             }
         } else {
@@ -1279,7 +1293,7 @@ __device__ __forceinline__ int lds_acquire(uint32_t a) { int r; asm volatile("ld
 __device__ __forceinline__ void sts_release(uint32_t a, int v) { asm volatile("st.release.cta.shared.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ pc pc_of(uint32_t lo, uint32_t hi) { pc r; asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "r"(lo), "r"(hi)); return r; }
 
-template <int INNER, bool TWT = true>
+template <int INNER, bool TWT = true, bool TMA_STORE = true>
 __global__ void __launch_bounds__(ColTmaCfg::threads, 1)
 col_pass_tma_kres(const __grid_constant__ ColParams p, const __grid_constant__ CUtensorMap tm_ld, const __grid_constant__ CUtensorMap tm_st)
 {
@@ -1362,6 +1376,7 @@ col_pass_tma_kres(const __grid_constant__ ColParams p, const __grid_constant__ C
     const int J = Mfull * D + (Mc - Mfull) * Dl;                               // items of this CTA
     auto chunk_len = [&](int m) { return m < Mfull ? D : Dl; };
     auto issue_load = [&](int m, int d, int gi) {
+        if (NDC_EXP_FLAG(1)) return;
         const uint32_t q = cta + (uint32_t)m * G, u = q / blocks, ib = q - u * blocks, t = u * (uint32_t)D + (uint32_t)d;
         const uint32_t mb = mb0 + 8 * gi;
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"((uint32_t)(C::p_elems * 8)) : "memory");
@@ -1395,13 +1410,14 @@ col_pass_tma_kres(const __grid_constant__ ColParams p, const __grid_constant__ C
     if (tid == 0 && J > 0) issue_load(0, 0, 0);
     uint32_t parity = 0, sparity = 0;
     const int nst = (F - p.skip) / p.store_rows;
+    (void)nst;
     int m = 0, d = g, start = 0, m_checked = 0;      // chunk, position in it, CTA item index of the chunk's first item; the newest chunk whose slot this thread knows complete
     while (m < Mc && d >= chunk_len(m)) { d -= chunk_len(m); start += chunk_len(m); m++; }
     for (int j = g; j < J; j += 2) {
         const uint32_t q = cta + (uint32_t)m * G, u = q / blocks, ib = q - u * blocks, t = u * (uint32_t)D + (uint32_t)d;
         const bool carries_part = d < K::parts && m + 1 < Mc;      // group-uniform
         pc v[32];
-        mbar_wait(mbg, parity);
+        if (!NDC_EXP_FLAG(1)) mbar_wait(mbg, parity);
         parity ^= 1;
 #pragma unroll
         for (int jj = 0; jj < 32; jj++) v[jj] = lds_pc(sP + ((i + 32 * jj) * 8 + c) * 8);
@@ -1450,18 +1466,27 @@ col_pass_tma_kres(const __grid_constant__ ColParams p, const __grid_constant__ C
 #pragma unroll
         for (int ii = 0; ii < Tc; ii++) v[ii] = lds_pc(sX + (i * pitch + ii * 8 + c) * 8);
         pk::dft<true, E>(v);                         // v[jj] = row i + 32 jj
+        if constexpr (!TMA_STORE) {
+            // A/B variant (NDCONV_COL_STG): the results leave straight from the registers as 64-byte row segments per 8 lanes, so the TMA
+            // unit moves the loads only (the exchange reads above were consumed by the last butterfly; the next item's first barrier orders
+            // its writes to the exchange buffer behind them)
+            cf *gt = p.ws + ((int64_t)NDC_RING_TILE(t) * F + i) * inner + ib * 8 + c;
+#pragma unroll
+            for (int jj = 0; jj < 32; jj++) if (i + 32 * jj >= p.skip) st_pc(gt + (int64_t)(32 * jj) * inner, v[jj]);
+        } else {
         bar_group(1 + g);                            // exchange reads done: the buffer becomes the dense [row][8] store staging
 #pragma unroll
         for (int jj = 0; jj < 32; jj++) sts_pc(sX + ((i + 32 * jj) * 8 + c) * 8, v[jj]);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         bar_group(1 + g);
-        if (lt == 0) {
+        if (lt == 0 && !NDC_EXP_FLAG(2)) {
             for (int b = 0; b < nst; b++) {
                 const int r = p.skip + b * p.store_rows;
                 asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
                              ::"l"(reinterpret_cast<uint64_t>(&tm_st)), "r"((int)(ib * 8)), "r"((int)(NDC_RING_TILE(t) * F + r)), "r"(sX + r * 64) : "memory");
             }
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
         }
         if (carries_part) {
             // scratch -> the other slot, which chunk m - 1 was read from: the other group must be past the multiply of its last item there

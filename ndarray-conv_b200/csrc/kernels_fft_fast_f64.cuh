@@ -386,18 +386,19 @@ __global__ void __launch_bounds__(128, 4) row_inv_d(const __grid_constant__ RowP
         const int Kd1 = p.Kd[al];
         const int64_t mbase = (int64_t)cur.tl * p.V[al];
         if (p.s[al] == 1) {
-            const int64_t obase = cur.orow + mbase - (Kd1 - 1);
-            const bool vec_ok = (obase & 1) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0;
+            double *outp = p.out + (cur.orow + mbase - (Kd1 - 1));                         // tile sample i -> outp[i] (fast::keep_range, kernels_fft_fast.cuh)
+            const int64_t room = p.O[al] - (mbase - (Kd1 - 1));
+            const int i0 = 2 * t;
+            const fast::KeepRange kr = fast::keep_range<2 * T>(Kd1 - 1, room < (int64_t)(2 * L) ? (int)room : 2 * L, i0);
+            const bool vec_ok = (reinterpret_cast<uintptr_t>(outp) & 15) == 0;
+            double *o = outp + i0;
 #pragma unroll
             for (int j = 0; j < R1; j++) {
-                const int i = 2 * (t + T * j);
-                const int64_t o_lo = mbase + i - (Kd1 - 1);
-                const bool ok0 = i >= Kd1 - 1 && o_lo < p.O[al];
-                const bool ok1 = i + 1 >= Kd1 - 1 && o_lo + 1 < p.O[al];
-                if (vec_ok && ok0 && ok1) *reinterpret_cast<double2 *>(p.out + cur.orow + o_lo) = make_double2(v[j].re, v[j].im);
+                const bool ok0 = j >= kr.ja0 && j < kr.jb0, ok1 = j >= kr.ja1 && j < kr.jb1;
+                if (vec_ok && ok0 && ok1) *reinterpret_cast<double2 *>(o + 2 * T * j) = make_double2(v[j].re, v[j].im);
                 else {
-                    if (ok0) p.out[cur.orow + o_lo] = v[j].re;
-                    if (ok1) p.out[cur.orow + o_lo + 1] = v[j].im;
+                    if (ok0) o[2 * T * j] = v[j].re;
+                    if (ok1) o[2 * T * j + 1] = v[j].im;
                 }
             }
         } else {
