@@ -127,6 +127,7 @@ struct RowParams {
     // same-shape batch (a leading axis of kernel extent 1 folded away by the host): problem b reads x + b * xstr_batch, its tiles follow
     // those of problem b - 1 in the workspace and its output rows follow in `out`; the batch index is the outermost tile coordinate
     int64_t xstr_batch;
+    FastDiv fd_rpt, fd_nt[3], fd_F[3];         // row_fwd: exact division by rows_per_tile / ntiles[a] / F[a] as multiply + shift (four run-time divisions per row were ~80 instructions)
     int pf_mode;                               // row_fwd, experiments: where the next row's samples are requested into L2 (0 never, 1 before this row's loads, 2 after its exchange)
 };
 
@@ -153,17 +154,19 @@ template <int N> __device__ __forceinline__ RowSrcInfo resolve_fwd_row(const Row
     if (!r.active) return r;
     // 32-bit index arithmetic (the host only takes this path when the work count fits; 64-bit division is ~5x dearer)
     const uint32_t w32 = (uint32_t)w, rpt = (uint32_t)p.rows_per_tile;
-    const uint32_t tile = w32 / rpt;
+    const uint32_t tile = (uint32_t)fdiv((int)w32, p.fd_rpt);
     uint32_t row = w32 - tile * rpt;
     r.dst = p.ws + (int64_t)NDC_RING_TILE(tile) * p.tile_elems + (int64_t)row * pitch;
     uint32_t tt = tile;
-    const uint32_t tl = tt % (uint32_t)p.ntiles[N - 1]; tt /= (uint32_t)p.ntiles[N - 1];
+    const uint32_t ql = (uint32_t)fdiv((int)tt, p.fd_nt[N - 1]);
+    const uint32_t tl = tt - ql * (uint32_t)p.ntiles[N - 1]; tt = ql;
     r.cl0 = (int64_t)tl * p.V[N - 1];
     int64_t c[2] = {0, 0};
 #pragma unroll
     for (int a = N - 2; a >= 0; a--) {
-        const uint32_t ta = tt % (uint32_t)p.ntiles[a]; tt /= (uint32_t)p.ntiles[a];
-        const uint32_t ra = row % (uint32_t)p.F[a]; row /= (uint32_t)p.F[a];
+        const uint32_t qt = (uint32_t)fdiv((int)tt, p.fd_nt[a]), qr = (uint32_t)fdiv((int)row, p.fd_F[a]);
+        const uint32_t ta = tt - qt * (uint32_t)p.ntiles[a]; tt = qt;
+        const uint32_t ra = row - qr * (uint32_t)p.F[a]; row = qr;
         c[a] = (int64_t)ta * p.V[a] + ra;
         if (c[a] >= p.P[a]) r.beyond = true;
     }

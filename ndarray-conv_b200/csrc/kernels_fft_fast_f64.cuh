@@ -39,6 +39,10 @@ template <bool INV, int RDX> __device__ __forceinline__ void dftd(cd *v)
 }
 __device__ __forceinline__ cd ld_cd(const cd *p) { const double2 q = *reinterpret_cast<const double2 *>(p); return cd{q.x, q.y}; }
 __device__ __forceinline__ void st_cd(cd *p, cd v) { *reinterpret_cast<double2 *>(p) = make_double2(v.re, v.im); }
+// dst[k * dst_stride] = v[k] * tw[k * tw_stride] (CONJ: times the conjugate), k < N, both in shared memory, with the twiddles fetched B at
+// a time ahead of the stores that follow them (fast::twiddle_store: the compiler cannot hoist a shared-memory load over a shared-memory store)
+template <int N, bool CONJ, int B = 4>
+__device__ __forceinline__ void twiddle_store_d(const cd *v, const cd *tw, int tw_stride, cd *dst, int dst_stride);
 __device__ __forceinline__ double shfl_d(double x, int src) { return __shfl_sync(0xffffffffu, x, src); }
 
 struct RowParamsD {
@@ -57,6 +61,19 @@ struct RowParamsD {
     int64_t rows_per_tile, tile_elems;         // prod of the outer F ; rows_per_tile * (L + 8)
     int64_t xstr_batch;                        // same-shape batch (see fast::RowParams)
 };
+
+template <int N, bool CONJ, int B>
+__device__ __forceinline__ void twiddle_store_d(const cd *v, const cd *tw, int tw_stride, cd *dst, int dst_stride)
+{
+#pragma unroll
+    for (int k0 = 0; k0 < N; k0 += B) {
+        cd w[B];
+#pragma unroll
+        for (int e = 0; e < B; e++) if (k0 + e < N) w[e] = ld_cd(tw + (k0 + e) * tw_stride);
+#pragma unroll
+        for (int e = 0; e < B; e++) if (k0 + e < N) st_cd(dst + (k0 + e) * dst_stride, CONJ ? cmulc(v[k0 + e], w[e]) : cmul(v[k0 + e], w[e]));
+    }
+}
 
 template <int T> struct RowCfgD {
     static constexpr int L = R1 * T, M = R1 / T, G = 32 / T;          // complex length, radix-T butterflies per lane, rows per warp
@@ -207,8 +224,7 @@ __global__ void __launch_bounds__(128, 4) row_fwd_d(const __grid_constant__ RowP
             }
         }
         dftd<false, R1>(v);                                               // over j -> k1
-#pragma unroll
-        for (int k1 = 0; k1 < R1; k1++) st_cd(sb + k1 * (T + 1) + t, cmul(v[k1], ld_cd(s_tw + k1 * T + t)));
+        twiddle_store_d<R1, false>(v, s_tw + t, T, sb + t, T + 1);
         __syncwarp();
 #pragma unroll
         for (int m = 0; m < M; m++)
@@ -373,8 +389,7 @@ __global__ void __launch_bounds__(128, 4) row_inv_d(const __grid_constant__ RowP
         for (int m = 0; m < M; m++) dftd<true, T>(v + m * T);
 #pragma unroll
         for (int m = 0; m < M; m++)
-#pragma unroll
-            for (int i = 0; i < T; i++) st_cd(sb + (t + T * m) * (T + 1) + i, cmulc(v[m * T + i], ld_cd(s_tw + i * R1 + (t + T * m))));
+            twiddle_store_d<T, true>(v + m * T, s_tw + (t + T * m), R1, sb + (t + T * m) * (T + 1), 1);
         __syncwarp();
 #pragma unroll
         for (int k1 = 0; k1 < R1; k1++) v[k1] = ld_cd(sb + k1 * (T + 1) + t);
@@ -488,8 +503,7 @@ __global__ void __launch_bounds__(ColCfgD<E, Tc>::threads, ColCfgD<E, Tc>::min_b
             for (int j = 0; j < E; j++) v[j] = ld_cd(S + (i + Tc * j) * 8 + c);
             __syncthreads();
             dftd<false, E>(v);
-#pragma unroll
-            for (int k1 = 0; k1 < E; k1++) st_cd(S + k1 * pitch + i * 8 + c, cmul(v[k1], ld_cd(s_tw + k1 * Tc + i)));
+            twiddle_store_d<E, false>(v, s_tw + i, Tc, S + i * 8 + c, pitch);
             __syncthreads();
 #pragma unroll
             for (int m = 0; m < Mc; m++)
@@ -523,8 +537,7 @@ __global__ void __launch_bounds__(ColCfgD<E, Tc>::threads, ColCfgD<E, Tc>::min_b
             // square case: the rows this thread holds (i + E k2) are also the rows the forward-structured flow starts from
             dftd<true, E>(v);
             __syncthreads();                               // every thread has finished reading S
-#pragma unroll
-            for (int n1 = 0; n1 < E; n1++) st_cd(S + n1 * pitch + i * 8 + c, cmulc(v[n1], ld_cd(s_tw + n1 * Tc + i)));
+            twiddle_store_d<E, true>(v, s_tw + i, Tc, S + i * 8 + c, pitch);
             __syncthreads();
 #pragma unroll
             for (int ii = 0; ii < Tc; ii++) v[ii] = ld_cd(S + i * pitch + ii * 8 + c);
@@ -536,8 +549,7 @@ __global__ void __launch_bounds__(ColCfgD<E, Tc>::threads, ColCfgD<E, Tc>::min_b
             __syncthreads();                               // every thread has finished reading S
 #pragma unroll
             for (int m = 0; m < Mc; m++)
-#pragma unroll
-                for (int ii = 0; ii < Tc; ii++) st_cd(S + (i + Tc * m) * pitch + ii * 8 + c, cmulc(v[m * Tc + ii], ld_cd(s_twT + ii * E + (i + Tc * m))));
+                twiddle_store_d<Tc, true>(v + m * Tc, s_twT + (i + Tc * m), E, S + (i + Tc * m) * pitch + c, 8);
             __syncthreads();
 #pragma unroll
             for (int k1 = 0; k1 < E; k1++) v[k1] = ld_cd(S + k1 * pitch + i * 8 + c);
