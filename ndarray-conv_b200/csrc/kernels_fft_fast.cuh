@@ -37,7 +37,7 @@ namespace fast {
 DEV void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
 DEV void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
-// Experiments only (tools/exp/ring_bound.sh builds a second library with -DNDCONV_EXP_RING): every tile's spectra land in slot
+// Experiments only (tools/exp/build_ring_lib.sh builds a second library with -DNDCONV_EXP_RING): every tile's spectra land in slot
 // tile % ring of the workspace, so the workspace traffic of each pass stays in L2 -- RESULTS ARE GARBAGE; the timings bound what a
 // fused, L2-resident pipeline could reach.  The product library is built without the macro.
 #ifdef NDCONV_EXP_RING
