@@ -292,6 +292,13 @@ __global__ void __launch_bounds__(128, 4) row_fwd(const __grid_constant__ RowPar
                 // rows of a small padded problem: every pair of them through border_pair cost c3 12 us)
                 const float rowval = ri.has_const ? ri.cval : 0.f;
                 const bool live = ri.active && !ri.beyond;
+                if (!live || (rowval == 0.f && p.cfront[al] == 0.f && p.cback[al] == 0.f)) {
+                    // identically zero (a Zeros border row, a never-written plane, a row beyond the padded extent; no non-zero constant border
+                    // of the last axis): such a row only comes here when it shares its warp with rows that do have samples (T < 32) -- the warp
+                    // runs both branches one after the other, so this one must cost nothing (c2 with Zeros borders: 30 us against 27 with Reflect)
+#pragma unroll
+                    for (int j = 0; j < 32; j++) v[j] = pk::mk(0.f, 0.f);
+                } else
 #pragma unroll
                 for (int j = 0; j < 32; j++) {
                     const int64_t cl = ri.cl0 + 2 * (t + T * j);
