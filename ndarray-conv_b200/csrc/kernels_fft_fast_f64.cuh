@@ -192,6 +192,11 @@ __global__ void __launch_bounds__(128, 4) row_fwd_d(const __grid_constant__ RowP
                 // rows of a small padded problem: every pair of them through border_pair cost c3 12 us)
                 const double rowval = ri.has_const ? ri.cval : 0.0;
                 const bool live = ri.active && !ri.beyond;
+                if (!live || (rowval == 0.0 && p.cfront[al] == 0.0 && p.cback[al] == 0.0)) {
+                    // identically zero: only reached when the row shares its warp with rows that do have samples, so it must cost nothing (see fast::row_fwd)
+#pragma unroll
+                    for (int j = 0; j < R1; j++) v[j] = cd{0.0, 0.0};
+                } else
 #pragma unroll
                 for (int j = 0; j < R1; j++) {
                     const int64_t cl = ri.cl0 + 2 * (t + T * j);
