@@ -53,3 +53,11 @@ def test_product_loader_rejects_emulation(pkg, emul_lib):
     src = (ROOT / "ndarray-conv_b200" / "__init__.py").read_text()
     assert "refusing to load a host-emulation build" in src
     assert "oracle" not in "".join(l for l in src.splitlines() if l.strip().startswith(("import", "from")))
+
+
+def test_product_library_is_not_the_experimental_build(pkg):
+    """tools/exp/build_ring_lib.sh builds a library with -DNDCONV_EXP_RING whose results are wrong by construction (timing experiments
+    of DESIGN.md section 9).  The in-tree product library must never be that build: its environment switches do not exist in it."""
+    blob = Path(pkg.LIB_PATH).read_bytes()
+    assert b"NDCONV_EXP_RING_TILES" not in blob and b"NDCONV_EXP_FLAGS" not in blob
+    assert b"ndconv_conv_fft" in blob
