@@ -119,12 +119,25 @@ __device__ __forceinline__ void blocked_loop(uint32_t tile_addr16, const T *s_rw
                 if (c < nv) raw = LdsRaw<16>::ld(a + 16u * (uint32_t)c);
                 memcpy(&buf[c * VN], &raw, 16);
             }
-#pragma unroll
-            for (int v = 0; v < kRowTaps; v++) {
+            // taps in ascending order.  4-byte elements: the tail groups [4, 6) and [6, 8) sit behind uniform branches on the row length, so
+            // a 5-tap row issues 24 multiply-adds instead of 32 with a third of them predicated off -- predicated-off instructions still
+            // take their issue slots, and this loop is bound by issue: 256x1024x1024 i32 k = 3x5x5 2.41 -> 2.14 ms,
+            // f32 k = 3x3x3 1.79 -> 1.34 ms, bit-identical; 7-tap rows pay the two branches (8192^2 k = 7x7 f32 616 -> 633 us).  Measured and
+            // rejected: three straight-line blocks of 4 / 6 / 8 taps (i32 k = 5: 2.49 ms), and the branches for 8-byte elements (+3 %).
+            auto tap = [&](int v) {
                 if ((mask >> v) & 1u) {
 #pragma unroll
                     for (int j = 0; j < R; j++) acc[q][j] = Elem<T>::mac(acc[q][j], buf[SHIFT + j * S2 + v * D2], w[v]);
                 }
+            };
+            static_assert(kRowTaps == 8, "tap groups below");
+            if constexpr (sizeof(T) == 4) {
+                tap(0); tap(1); tap(2); tap(3);
+                if (k2 > 4) { tap(4); tap(5); }
+                if (k2 > 6) { tap(6); tap(7); }
+            } else {
+#pragma unroll
+                for (int v = 0; v < kRowTaps; v++) tap(v);
             }
             a += (uint32_t)step0_bytes;
         }
